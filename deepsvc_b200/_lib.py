@@ -1,0 +1,84 @@
+"""ctypes binding of the C ABI declared in ``include/deepsvc_b200.h``.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (plain nvcc,
+``-gencode arch=compute_100a,code=sm_100a``).  There is NO fallback: if the library
+is missing, or a launcher reports an error, the calling op raises.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int32, c_int64, c_float, c_void_p, c_char_p, c_size_t
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdeepsvc_b200.so")
+
+FLOW_MUL_RECIPROCAL = 0
+FLOW_TRUE_DIVIDE = 1
+WARP_AUTO, WARP_GATHER, WARP_TMA = 0, 1, 2
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+EB_PARAMS_PER_CHANNEL = 60
+
+_P = c_void_p
+
+# name -> (restype, argtypes); mirrors include/deepsvc_b200.h one to one
+SIGNATURES = {
+    "dsvc_abi_version": (c_int, []),
+    "dsvc_error_string": (c_char_p, [c_int]),
+    "dsvc_device_arch": (c_int, []),
+    "dsvc_warp_fwd_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
+                                  c_float, c_float, c_float, c_float, c_int, c_int, c_int, _P]),
+    "dsvc_warp_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
+                                  c_float, c_float, c_float, c_float, c_int, c_int, _P]),
+    "dsvc_reduce_slots": (c_int, [c_int64, c_int64]),
+    "dsvc_gc_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P,
+                                c_float, c_float, c_int64, c_int64,
+                                c_int64, c_int64, c_int64, c_int64, _P]),
+    "dsvc_gc_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float,
+                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P]),
+    "dsvc_eb_reduce_slots": (c_int, [c_int, c_int, c_int]),
+    "dsvc_eb_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
+    "dsvc_eb_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
+    "dsvc_bits_finalize_f64": (c_int, [_P, _P, _P, _P, c_int, _P]),
+}
+
+_lib = None
+
+
+class DeepSVCNativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the native library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise DeepSVCNativeError(
+            f"deepsvc_b200 native library not found at {LIB_PATH}; build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dsvc_abi_version() != 1:
+        raise DeepSVCNativeError("deepsvc_b200 ABI version mismatch; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(err: int, what: str):
+    if err != 0:
+        msg = load().dsvc_error_string(err)
+        raise DeepSVCNativeError(f"{what} failed: CUDA error {err} "
+                                 f"({msg.decode() if msg else 'unknown'})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL for None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

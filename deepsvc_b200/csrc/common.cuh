@@ -1,0 +1,68 @@
+// Shared device helpers for the deepsvc_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifndef DSVC_NUM_SMS
+#define DSVC_NUM_SMS 148  // B200: 2 dies x 74 SMs
+#endif
+
+#define DSVC_CHECK_ARG(cond) \
+    do {                     \
+        if (!(cond)) return (int)cudaErrorInvalidValue; \
+    } while (0)
+
+#define DSVC_RETURN_LAST() return (int)cudaGetLastError()
+
+namespace dsvc {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum in fixed order (warp shuffle tree, then warp 0 over the per-warp
+// partials). Result valid in thread 0. `smem` must hold blockDim.x/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double r = 0.0;
+    if (wid == 0) {
+        r = lane < nw ? smem[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+__host__ __device__ __forceinline__ bool aligned16(const void* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// streaming 128-bit load / store (no L1 allocation: every element is touched once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream1(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+}  // namespace dsvc

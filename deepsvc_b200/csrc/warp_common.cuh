@@ -1,0 +1,57 @@
+// Coordinate arithmetic of the reference's backward warp, restated op for op.
+//
+// Reference: /root/reference/modules.py:25-62 (torch_warp) -> F.grid_sample(bilinear,
+// border, align_corners=True) -> ATen grid_sampler_2d (GridSampler.cuh:21-57
+// grid_sampler_unnormalize / clip_coordinates, GridSampler.cu forward/backward
+// kernels).  Every fp32 rounding step of that chain is kept (explicit _rn
+// intrinsics forbid FMA contraction across normalise / add / unnormalise), because
+// a "direct" x + flow formulation differs by up to 2e-4 at 1080p.
+#pragma once
+#include "common.cuh"
+
+namespace dsvc {
+
+struct WarpParams {
+    int B, C, H, W;
+    float sx, sy;          // (W-1)/2, (H-1)/2 as fp32
+    float inv_sx, inv_sy;  // fp32 reciprocals as ATen's CUDA div-by-scalar computes them
+    int flow_mode;         // DSVC_FLOW_MUL_RECIPROCAL / DSVC_FLOW_TRUE_DIVIDE
+};
+
+struct Taps {
+    int x0, y0;            // north-west tap (always inside the image)
+    bool x1ok, y1ok;       // east / south taps inside the image
+    float nw, ne, sw, se;  // bilinear weights, ATen order of operations
+};
+
+// normalised grid value -> clamped source coordinate (align_corners=True, border)
+__device__ __forceinline__ float source_coord(float lin, float fl, float s, float inv_s,
+                                              int flow_mode, int size) {
+    const float fs = flow_mode ? __fdiv_rn(fl, s) : __fmul_rn(fl, inv_s);  // modules.py:54-55
+    const float g = __fadd_rn(lin, fs);                                    // modules.py:57
+    // grid_sampler_unnormalize: ((g + 1) / 2) * (size - 1)
+    float c = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    // clip_coordinates: min(size - 1, max(c, 0))
+    c = fminf((float)(size - 1), fmaxf(c, 0.0f));
+    return c;
+}
+
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
+    Taps t;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    t.x0 = (int)fx0;
+    t.y0 = (int)fy0;
+    t.x1ok = t.x0 + 1 < W;
+    t.y1ok = t.y0 + 1 < H;
+    const float wx0 = __fsub_rn(fx0 + 1.0f, ix);  // ix_se - ix
+    const float wx1 = __fsub_rn(ix, fx0);         // ix - ix_nw
+    const float wy0 = __fsub_rn(fy0 + 1.0f, iy);
+    const float wy1 = __fsub_rn(iy, fy0);
+    t.nw = __fmul_rn(wx0, wy0);
+    t.ne = __fmul_rn(wx1, wy0);
+    t.sw = __fmul_rn(wx0, wy1);
+    t.se = __fmul_rn(wx1, wy1);
+    return t;
+}
+
+}  // namespace dsvc

@@ -1,0 +1,276 @@
+// Backward bilinear warp (motion compensation), direct-gather kernels.
+//
+// Replaces /root/reference/modules.py:25-62 (torch_warp) and its autograd.
+// These kernels read the four taps straight through the read-only path; the
+// shared-memory/TMA-staged forward lives in warp_tma.cu and is preferred when the
+// shape allows.  HBM-bound op: one launch reads input + flow once and writes out
+// once (4*B*H*W*(2C+2) algorithmic bytes); coordinates and weights are computed
+// once per pixel and reused for every channel.
+#include "warp_common.cuh"
+#include "../../include/deepsvc_b200.h"
+
+namespace dsvc {
+
+// ------------------------------------------------------------------ NCHW forward
+// CTA = 32 x 8 output pixels (one warp per 128-byte row segment, so that the
+// y/y+1 taps of neighbouring warps hit the same L1 lines), channels [c0, c0+cpc).
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+warp_fwd_nchw_gather(const float* __restrict__ in, const float* __restrict__ flow,
+                     float* __restrict__ out, const float* __restrict__ lin_x,
+                     const float* __restrict__ lin_y, WarpParams p, int cpc, int nchunk) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z / nchunk;
+    const int c0 = (blockIdx.z - b * nchunk) * cpc;
+    if (x >= p.W || y >= p.H) return;
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix = (size_t)y * p.W + x;
+    const float* fl = flow + (size_t)b * 2 * plane + pix;
+    const float fx = __ldg(fl), fy = __ldg(fl + plane);
+    const float ix = source_coord(__ldg(lin_x + x), fx, p.sx, p.inv_sx, p.flow_mode, p.W);
+    const float iy = source_coord(__ldg(lin_y + y), fy, p.sy, p.inv_sy, p.flow_mode, p.H);
+    const Taps t = make_taps(ix, iy, p.W, p.H);
+    const int o_nw = t.y0 * p.W + t.x0;
+    const int dx = t.x1ok ? 1 : 0;         // clamped so that the address stays legal;
+    const int dy = t.y1ok ? p.W : 0;       // the value is discarded when the tap is outside
+    const int cend = min(p.C, c0 + cpc);
+    const float* ip = in + ((size_t)b * p.C + c0) * plane + o_nw;
+    float* op = out + ((size_t)b * p.C + c0) * plane + pix;
+    int c = c0;
+    for (; c + UNROLL <= cend; c += UNROLL) {
+        float v[UNROLL][4];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const float* q = ip + (size_t)u * plane;
+            v[u][0] = __ldg(q);
+            v[u][1] = __ldg(q + dx);
+            v[u][2] = __ldg(q + dy);
+            v[u][3] = __ldg(q + dy + dx);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float acc = __fmul_rn(v[u][0], t.nw);
+            acc = t.x1ok ? fmaf(v[u][1], t.ne, acc) : acc;
+            acc = t.y1ok ? fmaf(v[u][2], t.sw, acc) : acc;
+            acc = (t.x1ok && t.y1ok) ? fmaf(v[u][3], t.se, acc) : acc;
+            st_stream1(op + (size_t)u * plane, acc);
+        }
+        ip += (size_t)UNROLL * plane;
+        op += (size_t)UNROLL * plane;
+    }
+    for (; c < cend; ++c) {
+        float acc = __fmul_rn(__ldg(ip), t.nw);
+        acc = t.x1ok ? fmaf(__ldg(ip + dx), t.ne, acc) : acc;
+        acc = t.y1ok ? fmaf(__ldg(ip + dy), t.sw, acc) : acc;
+        acc = (t.x1ok && t.y1ok) ? fmaf(__ldg(ip + dy + dx), t.se, acc) : acc;
+        st_stream1(op, acc);
+        ip += plane;
+        op += plane;
+    }
+}
+
+// ------------------------------------------------------------------ NHWC forward
+// channels_last: every tap is C contiguous floats -> pure 128-bit loads.  G lanes
+// cooperate on one pixel (G*16 bytes per tap per instruction), C % 4 == 0.
+template <int G>
+__global__ void __launch_bounds__(256)
+warp_fwd_nhwc(const float* __restrict__ in, const float* __restrict__ flow,
+              float* __restrict__ out, const float* __restrict__ lin_x,
+              const float* __restrict__ lin_y, WarpParams p) {
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t gpix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / G;  // b*H*W + y*W + x
+    const int sub = threadIdx.x % G;
+    if (gpix >= (size_t)p.B * plane) return;
+    const int b = (int)(gpix / plane);
+    const size_t pix = gpix - (size_t)b * plane;
+    const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);
+    const float* fl = flow + (size_t)b * 2 * plane + pix;
+    const float fx = __ldg(fl), fy = __ldg(fl + plane);
+    const float ix = source_coord(__ldg(lin_x + x), fx, p.sx, p.inv_sx, p.flow_mode, p.W);
+    const float iy = source_coord(__ldg(lin_y + y), fy, p.sy, p.inv_sy, p.flow_mode, p.H);
+    const Taps t = make_taps(ix, iy, p.W, p.H);
+    const int C4 = p.C >> 2;
+    const float4* base = reinterpret_cast<const float4*>(in) + (size_t)b * plane * C4;
+    const float4* q_nw = base + ((size_t)t.y0 * p.W + t.x0) * C4;
+    const size_t dx = t.x1ok ? (size_t)C4 : 0, dy = t.y1ok ? (size_t)p.W * C4 : 0;
+    float4* o = reinterpret_cast<float4*>(out) + gpix * C4;
+    const bool xe = t.x1ok, ys = t.y1ok, xy = t.x1ok && t.y1ok;
+    for (int c4 = sub; c4 < C4; c4 += G) {
+        const float4 a = __ldg(q_nw + c4);
+        const float4 bq = __ldg(q_nw + dx + c4);
+        const float4 cq = __ldg(q_nw + dy + c4);
+        const float4 d = __ldg(q_nw + dy + dx + c4);
+        float4 r;
+#define DSVC_TAP4(f)                                   \
+    r.f = __fmul_rn(a.f, t.nw);                        \
+    r.f = xe ? fmaf(bq.f, t.ne, r.f) : r.f;            \
+    r.f = ys ? fmaf(cq.f, t.sw, r.f) : r.f;            \
+    r.f = xy ? fmaf(d.f, t.se, r.f) : r.f;
+        DSVC_TAP4(x) DSVC_TAP4(y) DSVC_TAP4(z) DSVC_TAP4(w)
+#undef DSVC_TAP4
+        st_stream4(reinterpret_cast<float*>(o + c4), r);
+    }
+}
+
+// ------------------------------------------------------------------ backward (NCHW)
+// One thread per output pixel, all channels: grad_flow is a per-pixel reduction over
+// C kept in registers; grad_input taps are scattered with float reductions
+// (RED.ADD.F32, no return value).  Restates ATen grid_sampler_2d_backward_kernel
+// (bilinear / border / align_corners) followed by the division by sx, sy.
+template <bool NEED_GIN, bool NEED_GFLOW>
+__global__ void __launch_bounds__(256)
+warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
+              const float* __restrict__ flow, float* __restrict__ gin,
+              float* __restrict__ gflow, const float* __restrict__ lin_x,
+              const float* __restrict__ lin_y, WarpParams p) {
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int b = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix = (size_t)y * p.W + x;
+    const float* fl = flow + (size_t)b * 2 * plane + pix;
+    const float fx = __ldg(fl), fy = __ldg(fl + plane);
+    // unclipped coordinate, then clip_coordinates_set_grad
+    const float fsx = p.flow_mode ? __fdiv_rn(fx, p.sx) : __fmul_rn(fx, p.inv_sx);
+    const float fsy = p.flow_mode ? __fdiv_rn(fy, p.sy) : __fmul_rn(fy, p.inv_sy);
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(__ldg(lin_x + x), fsx), 1.0f), 0.5f),
+                         (float)(p.W - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(__ldg(lin_y + y), fsy), 1.0f), 0.5f),
+                         (float)(p.H - 1));
+    float gx_mult = (float)(p.W - 1) * 0.5f, gy_mult = (float)(p.H - 1) * 0.5f;
+    if (ix <= 0.0f) { ix = 0.0f; gx_mult = 0.0f; }
+    else if (ix >= (float)(p.W - 1)) { ix = (float)(p.W - 1); gx_mult = 0.0f; }
+    if (iy <= 0.0f) { iy = 0.0f; gy_mult = 0.0f; }
+    else if (iy >= (float)(p.H - 1)) { iy = (float)(p.H - 1); gy_mult = 0.0f; }
+    const Taps t = make_taps(ix, iy, p.W, p.H);
+    const float fx0 = (float)t.x0, fy0 = (float)t.y0;
+    const float wx0 = __fsub_rn(fx0 + 1.0f, ix), wx1 = __fsub_rn(ix, fx0);
+    const float wy0 = __fsub_rn(fy0 + 1.0f, iy), wy1 = __fsub_rn(iy, fy0);
+    const int o_nw = t.y0 * p.W + t.x0;
+    const int dx = t.x1ok ? 1 : 0, dy = t.y1ok ? p.W : 0;
+    const bool xe = t.x1ok, ys = t.y1ok, xy = t.x1ok && t.y1ok;
+    const float* gp = gout + (size_t)b * p.C * plane + pix;
+    const float* ip = in + (size_t)b * p.C * plane + o_nw;
+    float* gi = NEED_GIN ? gin + (size_t)b * p.C * plane + o_nw : nullptr;
+    float gix = 0.0f, giy = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < p.C; ++c) {
+        const float g = __ldg(gp);
+        if (NEED_GIN) {
+            atomicAdd(gi, __fmul_rn(t.nw, g));
+            if (xe) atomicAdd(gi + dx, __fmul_rn(t.ne, g));
+            if (ys) atomicAdd(gi + dy, __fmul_rn(t.sw, g));
+            if (xy) atomicAdd(gi + dy + dx, __fmul_rn(t.se, g));
+            gi += plane;
+        }
+        if (NEED_GFLOW) {
+            const float v_nw = __ldg(ip);
+            gix -= v_nw * wy0 * g;
+            giy -= v_nw * wx0 * g;
+            if (xe) {
+                const float v = __ldg(ip + dx);
+                gix += v * wy0 * g;
+                giy -= v * wx1 * g;
+            }
+            if (ys) {
+                const float v = __ldg(ip + dy);
+                gix -= v * wy1 * g;
+                giy += v * wx0 * g;
+            }
+            if (xy) {
+                const float v = __ldg(ip + dy + dx);
+                gix += v * wy1 * g;
+                giy += v * wx1 * g;
+            }
+            ip += plane;
+        }
+        gp += plane;
+    }
+    if (NEED_GFLOW) {
+        float* gf = gflow + (size_t)b * 2 * plane + pix;
+        const float ggx = __fmul_rn(gx_mult, gix), ggy = __fmul_rn(gy_mult, giy);
+        // autograd of flow / s: grad / s  (CUDA: grad * (1/s))
+        gf[0] = p.flow_mode ? __fdiv_rn(ggx, p.sx) : __fmul_rn(ggx, p.inv_sx);
+        gf[plane] = p.flow_mode ? __fdiv_rn(ggy, p.sy) : __fmul_rn(ggy, p.inv_sy);
+    }
+}
+
+}  // namespace dsvc
+
+using namespace dsvc;
+
+int dsvc_warp_fwd_tma_launch(const float* input, const float* flow, float* out,
+                             const float* lin_x, const float* lin_y, const WarpParams& p,
+                             bool force, cudaStream_t st);  // warp_tma.cu
+
+static int warp_args_ok(const void* a, const void* b, const void* c, int B, int C, int H, int W,
+                        const void* lx, const void* ly) {
+    return a && b && c && lx && ly && B > 0 && C > 0 && H > 0 && W > 0 &&
+           (int64_t)H * W < (int64_t)1 << 30 && B <= 65535;
+}
+
+extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* out, int B, int C,
+                                 int H, int W, const float* lin_x, const float* lin_y, float sx,
+                                 float sy, float inv_sx, float inv_sy, int flow_mode, int layout,
+                                 int algo, void* stream) {
+    DSVC_CHECK_ARG(warp_args_ok(input, flow, out, B, C, H, W, lin_x, lin_y));
+    DSVC_CHECK_ARG(flow_mode == 0 || flow_mode == 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+    if (layout == DSVC_LAYOUT_NHWC) {
+        DSVC_CHECK_ARG(C % 4 == 0 && aligned16(input) && aligned16(out));
+        DSVC_CHECK_ARG(algo != DSVC_WARP_TMA);
+        const int C4 = C / 4;
+        const int G = C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1));
+        const size_t nthreads = (size_t)B * H * W * G;
+        const unsigned grid = (unsigned)((nthreads + 255) / 256);
+        switch (G) {
+            case 8: warp_fwd_nhwc<8><<<grid, 256, 0, st>>>(input, flow, out, lin_x, lin_y, p); break;
+            case 4: warp_fwd_nhwc<4><<<grid, 256, 0, st>>>(input, flow, out, lin_x, lin_y, p); break;
+            case 2: warp_fwd_nhwc<2><<<grid, 256, 0, st>>>(input, flow, out, lin_x, lin_y, p); break;
+            default: warp_fwd_nhwc<1><<<grid, 256, 0, st>>>(input, flow, out, lin_x, lin_y, p); break;
+        }
+        DSVC_RETURN_LAST();
+    }
+    DSVC_CHECK_ARG(layout == DSVC_LAYOUT_NCHW);
+    if (algo == DSVC_WARP_AUTO || algo == DSVC_WARP_TMA) {
+        const int r = dsvc_warp_fwd_tma_launch(input, flow, out, lin_x, lin_y, p,
+                                               algo == DSVC_WARP_TMA, st);
+        if (r != -1) return r;  // -1: shape not supported by the staged kernel -> gather
+        if (algo == DSVC_WARP_TMA) return (int)cudaErrorInvalidValue;
+    }
+    // channel chunk per CTA: enough CTAs to fill the machine, few flow re-reads
+    int cpc = C;
+    if (C > 16) cpc = 16;
+    const int nchunk = (C + cpc - 1) / cpc;
+    DSVC_CHECK_ARG((int64_t)B * nchunk <= 65535);
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B * nchunk);
+    if (cpc >= 4)
+        warp_fwd_nchw_gather<4><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
+    else
+        warp_fwd_nchw_gather<1><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
+    DSVC_RETURN_LAST();
+}
+
+extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,
+                                 float* grad_input, float* grad_flow, int B, int C, int H, int W,
+                                 const float* lin_x, const float* lin_y, float sx, float sy,
+                                 float inv_sx, float inv_sy, int flow_mode, int layout,
+                                 void* stream) {
+    DSVC_CHECK_ARG(warp_args_ok(grad_out, input, flow, B, C, H, W, lin_x, lin_y));
+    DSVC_CHECK_ARG(flow_mode == 0 || flow_mode == 1);
+    DSVC_CHECK_ARG(layout == DSVC_LAYOUT_NCHW);
+    if (!grad_input && !grad_flow) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B);
+    if (grad_input && grad_flow)
+        warp_bwd_nchw<true, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
+    else if (grad_input)
+        warp_bwd_nchw<true, false><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
+    else
+        warp_bwd_nchw<false, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
+    DSVC_RETURN_LAST();
+}

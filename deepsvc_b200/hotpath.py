@@ -1,0 +1,263 @@
+"""One P-frame of the DeepSVC warp + entropy hot path as a fixed launch sequence.
+
+``PFrameHotPath`` issues, for one frame, exactly the hot-path calls of
+``DeepSVC.forward`` (``video_model.py:27-71``) in the reference's order -- 4 SpyNet
+pyramid warps (``modules.py:167``), the 3-ch frame warp (``video_model.py:37``), the
+64-ch feature warp (``modules.py:429``), then per codec (mv, res) one
+EntropyBottleneck call (``image_model.py:155-162``) and 8 GaussianConditional slice
+calls (``:181-183``), and the bit sums (``video_model.py:39-42,53-56``) -- with the
+conv transforms removed (their outputs are supplied as tensors).
+
+All outputs are pre-allocated and every launcher argument is bound once, so a frame is
+25 kernel launches with no allocation and no synchronisation, and can be captured into
+a CUDA graph (``capture()`` / ``replay()``).
+"""
+import math
+
+import torch
+
+from . import _lib
+from .entropy import EntropyBottleneck, GaussianConditional, _common_rows
+from .warp import _base_grids, _scales
+
+NUM_SLICES = 8
+
+
+class PFrameHotPath:
+    def __init__(self, inputs: dict, models: dict, flow_mode=_lib.FLOW_MUL_RECIPROCAL,
+                 warp_algo=_lib.WARP_AUTO):
+        """inputs: tensors from ``synthetic.make_pframe_inputs`` already on one CUDA
+        device; models: {"mv": (EntropyBottleneck, GaussianConditional), "res": (...)}
+        (this package's drop-in classes, on the same device, eval mode)."""
+        self.lib = _lib.load()
+        self.inputs = inputs
+        self.models = models
+        dev = inputs["ref_frame"].device
+        self.device = dev
+        self.flow_mode = flow_mode
+        self.warp_algo = warp_algo
+        B, _, H, W = inputs["ref_frame"].shape
+        self.pixels = B * H * W
+        self._keep = []   # tensors the bound pointers refer to
+        self._calls = []  # (fn, args, name)
+        self.out = {}
+        self.n_launches = 0
+
+        # ---- warps
+        self.out["spynet"] = []
+        for img, fl in zip(inputs["pyr_img"], inputs["pyr_flow"]):
+            self.out["spynet"].append(self._bind_warp(img, fl))
+        self.out["warped_frame"] = self._bind_warp(inputs["ref_frame"], inputs["flow"])
+        self.out["warped_feature"] = self._bind_warp(inputs["feature"], inputs["flow"])
+
+        # ---- entropy: partial-sum buffer with one segment per codec
+        seg = [0]
+        plan = []
+        for name in ("mv", "res"):
+            eb, gc = models[name]
+            assert isinstance(eb, EntropyBottleneck) and isinstance(gc, GaussianConditional)
+            y, z = inputs[f"{name}_y"], inputs[f"{name}_z"]
+            Bz, Cz = z.shape[0], z.shape[1]
+            Sz = z.numel() // (Bz * Cz)
+            n_eb = self.lib.dsvc_eb_reduce_slots(Bz, Cz, Sz)
+            ys = y.chunk(NUM_SLICES, 1)
+            ss = inputs[f"{name}_scales"].chunk(NUM_SLICES, 1)
+            ms = inputs[f"{name}_means"].chunk(NUM_SLICES, 1)
+            slices = []
+            cnt = n_eb
+            for y_s, s_s, m_s in zip(ys, ss, ms):
+                rows, inner, st = _common_rows([y_s, s_s, m_s])
+                n = self.lib.dsvc_reduce_slots(rows, inner)
+                slices.append((y_s, s_s, m_s, rows, inner, st, n))
+                cnt += n
+            plan.append((name, eb, gc, z, (Bz, Cz, Sz), n_eb, slices))
+            seg.append(seg[-1] + cnt)
+        self.partials = torch.zeros(seg[-1], dtype=torch.float64, device=dev)
+        self.seg = torch.tensor(seg, dtype=torch.int32, device=dev)
+        self.scales = torch.full((2,), -1.0 / (math.log(2) * self.pixels), dtype=torch.float64,
+                                 device=dev)
+        self.bpp = torch.zeros(2, dtype=torch.float64, device=dev)  # [bpp_mv, bpp_res]
+        esz = self.partials.element_size()
+        for ci, (name, eb, gc, z, (Bz, Cz, Sz), n_eb, slices) in enumerate(plan):
+            off = seg[ci]
+            packed = eb.packed_params(False)
+            z_hat = torch.empty_like(z)
+            self._keep += [packed, z_hat]
+            self.out[f"{name}_z_hat"] = z_hat
+            self._calls.append((self.lib.dsvc_eb_fwd_f32, (
+                z.data_ptr(), None, packed.data_ptr(), None, None, z_hat.data_ptr(),
+                self.partials.data_ptr() + off * esz, eb._lik_bound, Bz, Cz, Sz), f"eb_{name}"))
+            off += n_eb
+            sb, lb = gc._bounds()
+            yh_slices = []
+            for (ys_, ss_, ms_, rows, inner, st, n) in slices:
+                # outputs of one call are dense [rows, inner] (one tensor per slice call,
+                # like the reference's y_hat_slices list, image_model.py:190)
+                yh = torch.empty(ys_.shape, dtype=torch.float32, device=dev)
+                yh_slices.append(yh)
+                self._calls.append((self.lib.dsvc_gc_fwd_f32, (
+                    ys_.data_ptr(), ss_.data_ptr(), ms_.data_ptr(), None,
+                    None, None, yh.data_ptr(), None, None, None, 0,
+                    self.partials.data_ptr() + off * esz, sb, lb, rows, inner,
+                    st[0], st[1], st[2], 0), f"gc_{name}"))
+                off += n
+            self.out[f"{name}_y_hat_slices"] = yh_slices
+            assert off == seg[ci + 1]
+        self._calls.append((self.lib.dsvc_bits_finalize_f64, (
+            self.partials.data_ptr(), self.seg.data_ptr(), self.scales.data_ptr(),
+            self.bpp.data_ptr(), 2), "bits_finalize"))
+        self.n_launches = len(self._calls)
+        self._graph = None
+
+    def _bind_warp(self, inp, flow):
+        B, C, H, W = inp.shape
+        out = torch.empty_like(inp)
+        lin_x, lin_y = _base_grids(inp.device, H, W)
+        sx, sy, inv_sx, inv_sy = _scales(H, W)
+        self._keep += [out, lin_x, lin_y]
+        self._calls.append((self.lib.dsvc_warp_fwd_f32, (
+            inp.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, lin_x.data_ptr(),
+            lin_y.data_ptr(), sx, sy, inv_sx, inv_sy, self.flow_mode, _lib.LAYOUT_NCHW,
+            self.warp_algo), f"warp_c{C}_{H}x{W}"))
+        return out
+
+    def run(self):
+        """Enqueue the frame's launches on the current stream."""
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            for fn, args, name in self._calls:
+                err = fn(*args, st)
+                if err:
+                    _lib.check(err, name)
+
+    def capture(self):
+        """Capture ``run()`` into a CUDA graph (after a warm-up run on a side stream)."""
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.run()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self._graph = g
+        return g
+
+    def replay(self):
+        self._graph.replay()
+
+    def results(self):
+        """Outputs of the last run (device tensors) + bpp as python floats (synchronises)."""
+        bpp = self.bpp.tolist()
+        r = dict(self.out)
+        for name in ("mv", "res"):
+            r[f"{name}_y_hat"] = torch.cat(r[f"{name}_y_hat_slices"], 1)
+        r["bpp_mv"], r["bpp_res"], r["bpp"] = bpp[0], bpp[1], bpp[0] + bpp[1]
+        return r
+
+
+class HostSession:
+    """Host-buffer entry point of the path: ``process()`` takes one frame's inputs from
+    pinned HOST memory, runs the hot path on the device and delivers every result
+    (warped pyramids / frame / feature, y_hat, z_hat, bpp) back to pinned HOST memory.
+
+    Two device slots and three streams (H2D, compute, D2H) pipeline consecutive frames:
+    while frame i computes, frame i+1 uploads and frame i-1 downloads, so PCIe runs in
+    both directions at once.  ``process()`` is asynchronous; ``wait(slot)`` / ``drain()``
+    make a frame's host outputs readable.
+    """
+
+    SLOTS = 2
+
+    def __init__(self, host_inputs: dict, models: dict, device, flow_mode=_lib.FLOW_MUL_RECIPROCAL,
+                 warp_algo=_lib.WARP_AUTO):
+        self.device = device
+
+        def pin(t):
+            p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            p.copy_(t)
+            return p
+
+        self.host_in = {k: ([pin(t) for t in v] if isinstance(v, list) else pin(v))
+                        for k, v in host_inputs.items()}
+        self.s_h2d = torch.cuda.Stream(device)
+        self.s_comp = torch.cuda.Stream(device)
+        self.s_d2h = torch.cuda.Stream(device)
+        self.slots = []
+        for _ in range(self.SLOTS):
+            dev_in = {k: ([torch.empty(t.shape, dtype=t.dtype, device=device) for t in v]
+                          if isinstance(v, list) else torch.empty(v.shape, dtype=v.dtype, device=device))
+                      for k, v in self.host_in.items()}
+            with torch.cuda.stream(self.s_comp):
+                hp = PFrameHotPath(dev_in, models, flow_mode=flow_mode, warp_algo=warp_algo)
+                for k, v in self.host_in.items():  # first upload so that capture warm-up sees data
+                    for d, h in zip(dev_in[k] if isinstance(v, list) else [dev_in[k]],
+                                    v if isinstance(v, list) else [v]):
+                        d.copy_(h, non_blocking=True)
+                hp.capture()
+            outs = self._flat_outputs(hp)
+            host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+            self.slots.append({
+                "hp": hp, "dev_in": dev_in, "outs": outs, "host_out": host_out,
+                "h2d_done": torch.cuda.Event(), "comp_done": torch.cuda.Event(),
+                "d2h_done": torch.cuda.Event(), "used": False})
+        torch.cuda.synchronize(device)
+        self._pairs = []
+        for k, v in self.host_in.items():
+            self._pairs += [(k, i) for i in range(len(v))] if isinstance(v, list) else [(k, None)]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for k, v in self.host_in.items()
+                             for t in (v if isinstance(v, list) else [v]))
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["outs"])
+        self.frame = 0
+
+    @staticmethod
+    def _flat_outputs(hp):
+        o = hp.out
+        return (list(o["spynet"]) + [o["warped_frame"], o["warped_feature"]] +
+                list(o["mv_y_hat_slices"]) + [o["mv_z_hat"]] +
+                list(o["res_y_hat_slices"]) + [o["res_z_hat"]] + [hp.bpp])
+
+    def process(self, host_inputs: dict = None) -> int:
+        """Enqueue one frame.  `host_inputs` (pinned CPU tensors, same shapes) defaults to
+        the session's own pinned buffers.  Returns the slot whose host outputs will hold
+        this frame's results after ``wait(slot)``."""
+        src = self.host_in if host_inputs is None else host_inputs
+        si = self.frame % self.SLOTS
+        s = self.slots[si]
+        self.frame += 1
+        with torch.cuda.stream(self.s_h2d):
+            if s["used"]:
+                self.s_h2d.wait_event(s["comp_done"])  # slot inputs free again
+            for k, i in self._pairs:
+                d = s["dev_in"][k] if i is None else s["dev_in"][k][i]
+                h = src[k] if i is None else src[k][i]
+                d.copy_(h, non_blocking=True)
+            s["h2d_done"].record(self.s_h2d)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(s["h2d_done"])
+            if s["used"]:
+                self.s_comp.wait_event(s["d2h_done"])  # slot outputs downloaded
+            s["hp"].replay()
+            s["comp_done"].record(self.s_comp)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(s["comp_done"])
+            for d, h in zip(s["outs"], s["host_out"]):
+                h.copy_(d, non_blocking=True)
+            s["d2h_done"].record(self.s_d2h)
+        s["used"] = True
+        return si
+
+    def wait(self, slot: int):
+        self.slots[slot]["d2h_done"].synchronize()
+        return self.slots[slot]["host_out"]
+
+    def drain(self):
+        for s in self.slots:
+            if s["used"]:
+                s["d2h_done"].synchronize()
+
+    def host_bpp(self, slot: int):
+        out = self.wait(slot)
+        b = out[-1].tolist()
+        return b[0], b[1]

@@ -1,0 +1,95 @@
+"""Drop-in installation into an UNMODIFIED reference checkout.
+
+The reference has no plugin registry; its hot path is reached through three kinds of
+names:
+
+1. the module-level function ``modules.torch_warp``, imported *by name* into
+   ``video_model`` (``video_model.py:3``) -> both bindings are replaced;
+2. the ``gaussian_conditional`` / ``entropy_bottleneck`` attributes of every
+   ``ChannelSplitICIP2020ResB`` / ``ICIP2020ResB`` (``image_model.py:148-149``);
+3. the free function ``ste_round`` imported by name into ``image_model``
+   (``image_model.py:7``).
+"""
+import sys
+
+import torch
+
+from . import entropy as _entropy
+from . import warp as _warp
+
+_saved = {}
+
+
+def patch_reference(modules_mod=None, video_model_mod=None, image_model_mod=None):
+    """Rebind the reference's module-level names to this package's ops.  Modules are
+    looked up in ``sys.modules`` when not given (i.e. after ``import video_model``)."""
+    modules_mod = modules_mod or sys.modules.get("modules")
+    video_model_mod = video_model_mod or sys.modules.get("video_model")
+    image_model_mod = image_model_mod or sys.modules.get("image_model")
+    for mod in (modules_mod, video_model_mod):
+        if mod is not None and hasattr(mod, "torch_warp"):
+            _saved.setdefault((mod.__name__, "torch_warp"), mod.torch_warp)
+            mod.torch_warp = _warp.torch_warp
+    if image_model_mod is not None and hasattr(image_model_mod, "ste_round"):
+        _saved.setdefault((image_model_mod.__name__, "ste_round"), image_model_mod.ste_round)
+        image_model_mod.ste_round = _entropy.ste_round
+    return [k for k in _saved]
+
+
+def unpatch_reference():
+    for (mod_name, attr), fn in list(_saved.items()):
+        mod = sys.modules.get(mod_name)
+        if mod is not None:
+            setattr(mod, attr, fn)
+        del _saved[(mod_name, attr)]
+
+
+def _convert_gc(old):
+    new = _entropy.GaussianConditional(
+        None, scale_bound=float(old.lower_bound_scale.bound.item()),
+        tail_mass=float(old.tail_mass),
+        likelihood_bound=float(old.likelihood_lower_bound.bound.item())
+        if getattr(old, "use_likelihood_bound", True) else 0.0,
+        entropy_coder_precision=int(old.entropy_coder_precision))
+    dev = old.scale_bound.device if old.scale_bound is not None else torch.device("cpu")
+    new = new.to(dev)
+    for name in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"):
+        setattr(new, name, getattr(old, name).clone())
+    new.train(old.training)
+    return new
+
+
+def _convert_eb(old):
+    new = _entropy.EntropyBottleneck(
+        old.channels, tail_mass=old.tail_mass, init_scale=old.init_scale, filters=old.filters,
+        likelihood_bound=float(old.likelihood_lower_bound.bound.item())
+        if getattr(old, "use_likelihood_bound", True) else 0.0,
+        entropy_coder_precision=int(old.entropy_coder_precision))
+    new = new.to(old.quantiles.device)
+    for name in ("_offset", "_quantized_cdf", "_cdf_length"):
+        setattr(new, name, getattr(old, name).clone())
+    # share the very same Parameter objects so optimizers / checkpoints keep working
+    for name, p in old.named_parameters(recurse=False):
+        new._parameters[name] = p
+    new.train(old.training)
+    return new
+
+
+def swap_entropy_models(model: torch.nn.Module) -> int:
+    """Replace every compressai-style ``GaussianConditional`` / ``EntropyBottleneck``
+    submodule of `model` (e.g. a built ``DeepSVC``) by this package's drop-ins, keeping
+    parameters (shared), buffers, training flag and state_dict keys.  Returns the number
+    of modules swapped."""
+    n = 0
+    for parent in list(model.modules()):
+        for name, child in list(parent.named_children()):
+            if isinstance(child, (_entropy.GaussianConditional, _entropy.EntropyBottleneck)):
+                continue
+            cls = type(child).__name__
+            if cls == "GaussianConditional":
+                setattr(parent, name, _convert_gc(child))
+                n += 1
+            elif cls == "EntropyBottleneck":
+                setattr(parent, name, _convert_eb(child))
+                n += 1
+    return n

@@ -1,0 +1,146 @@
+"""Multi-GPU partitioning of the hot path.
+
+The path shards by independent units with NO data-path collective: within a GOP the
+P-frames are serially dependent (``ref_frame`` / ``feature`` carry,
+``test_video.py:368-369``), GOPs are independent (I-frame + ``feature=None`` reset at
+``i % GOP == 0``, ``test_video.py:296-297``) and sequences are independent (``:274``).
+Unit = (sequence, GOP).  One process per GPU; the only communication is the timing
+barrier / max-reduce and a gather of a few floats of metrics.  Training adds a
+data-parallel gradient all-reduce (``allreduce_gradients``).
+"""
+import os
+from dataclasses import dataclass
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class GopJob:
+    sequence: int
+    gop: int
+    first_frame: int
+    n_frames: int  # frames in the GOP, the first one is the I-frame
+
+    @property
+    def p_frames(self) -> int:
+        return max(self.n_frames - 1, 0)
+
+
+def make_gop_jobs(frames_per_sequence: Sequence[int], gop: int) -> List[GopJob]:
+    """Split every sequence into GOPs (``test_video.py:290-297``: frame i is an I-frame
+    iff i % GOP == 0)."""
+    jobs = []
+    for s, n in enumerate(frames_per_sequence):
+        for g, first in enumerate(range(0, n, gop)):
+            jobs.append(GopJob(s, g, first, min(gop, n - first)))
+    return jobs
+
+
+def assign_jobs(jobs: Sequence[GopJob], world_size: int) -> List[List[GopJob]]:
+    """Static longest-processing-time assignment (cost = P-frames in the GOP);
+    deterministic, identical on every rank."""
+    order = sorted(range(len(jobs)), key=lambda i: (-jobs[i].p_frames, i))
+    loads = [0] * world_size
+    out = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        out[r].append(jobs[i])
+        loads[r] += jobs[i].p_frames
+    for r in range(world_size):
+        out[r].sort(key=lambda j: (j.sequence, j.gop))
+    return out
+
+
+def balance(assignment: Sequence[Sequence[GopJob]]) -> float:
+    """mean load / max load: the scaling efficiency bound of a static partition."""
+    loads = [sum(j.p_frames for j in a) for a in assignment]
+    return (sum(loads) / len(loads)) / max(loads) if max(loads) else 1.0
+
+
+def dist_env():
+    """(rank, local_rank, world_size) from the torchrun environment (1 process = 1 GPU)."""
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def init_distributed(backend: str = None):
+    rank, local_rank, world = dist_env()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    return rank, local_rank, world
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Max of a per-rank scalar (device-side time of the slowest rank)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_metrics(local: dict):
+    """Per-rank metric dicts on every rank (a few floats; host side)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [local]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, local)
+    return out
+
+
+def allreduce_gradients(params, bucket_bytes: int = 32 << 20, clamp: float = None):
+    """Training-mode data-parallel gradient sync (the only collective on the path):
+    mean all-reduce of fp32 grads in flat buckets over NCCL/NVLink, issued
+    asynchronously and waited at the end; the reference's element-wise clamp to +-1
+    (``Learner.py:1687-1691``) is applied AFTER the reduction so that N GPUs x batch b
+    equals one GPU x batch N*b."""
+    params = [p for p in params if p.grad is not None]
+    if not params:
+        return 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    buckets, cur, size = [], [], 0
+    for p in params:
+        cur.append(p)
+        size += p.grad.numel() * p.grad.element_size()
+        if size >= bucket_bytes:
+            buckets.append(cur)
+            cur, size = [], 0
+    if cur:
+        buckets.append(cur)
+    pending = []
+    for b in buckets:
+        flat = torch.cat([p.grad.reshape(-1) for p in b])
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
+        pending.append((b, flat, work))
+    for b, flat, work in pending:
+        if work is not None:
+            work.wait()
+        if world > 1:
+            flat.div_(world)
+        if clamp is not None:
+            flat.clamp_(-clamp, clamp)
+        off = 0
+        for p in b:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+    return len(buckets)

@@ -1,0 +1,165 @@
+/*
+ * deepsvc_b200 -- C ABI of the B200 (sm_100a) warp + entropy P-frame hot path.
+ *
+ * Drop-in boundary for the DeepSVC structure/texture layer hot path.  The
+ * reference (LHB116/DeepSVC) is pure Python and has no FFI of its own; every
+ * entry point below names the reference callable whose arithmetic it replaces
+ * (file:line into the reference tree).  The Python host side
+ * (deepsvc_b200/*.py) binds these symbols with ctypes and mirrors the
+ * reference's signatures (torch_warp, GaussianConditional, EntropyBottleneck,
+ * ste_round); see INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the function name ends in _host;
+ *   - tensors are dense fp32, NCHW ("layout 0") unless stated; inputs are
+ *     borrowed and never written; outputs are caller-allocated;
+ *   - every launcher enqueues on `stream` (a cudaStream_t passed as void*),
+ *     performs no allocation and no synchronisation -> CUDA-graph capturable;
+ *   - return value: 0 on success, otherwise a cudaError_t value
+ *     (dsvc_error_string() gives the text); DSVC_ERR_INVALID_ARG (= 1 =
+ *     cudaErrorInvalidValue) for bad shapes / null pointers / misalignment.
+ *     There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef DEEPSVC_B200_H_
+#define DEEPSVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSVC_ABI_VERSION 1
+#define DSVC_ERR_INVALID_ARG 1
+
+/* ---- flow scaling arithmetic (modules.py:36-37 CPU branch, :54-55 CUDA branch) ----
+ * The reference divides the pixel flow by (W-1)/2 and (H-1)/2 with a python
+ * scalar.  ATen executes that as a true division on CPU and as a multiply by
+ * the fp32 reciprocal on CUDA; the two differ in the last bit, which moves the
+ * sampling coordinate by up to 1e-4 px at 1080p.  The caller picks which of
+ * the reference's two branches to reproduce. */
+#define DSVC_FLOW_MUL_RECIPROCAL 0 /* reference CUDA branch (default for the drop-in) */
+#define DSVC_FLOW_TRUE_DIVIDE 1    /* reference CPU branch */
+
+/* ---- warp algorithm selector ---- */
+#define DSVC_WARP_AUTO 0   /* TMA-staged tiles when shape/alignment allow, else gather */
+#define DSVC_WARP_GATHER 1 /* direct read-only-path gather */
+#define DSVC_WARP_TMA 2    /* force shared-memory/TMA staging (error if unsupported) */
+
+#define DSVC_LAYOUT_NCHW 0
+#define DSVC_LAYOUT_NHWC 1 /* torch.channels_last */
+
+int dsvc_abi_version(void);
+const char* dsvc_error_string(int err);
+/* Compute capability of the current device as major*10+minor (100 on B200), <0 on error. */
+int dsvc_device_arch(void);
+
+/* Backward bilinear warp, border clamp, align_corners=True.
+ * Replaces modules.py:25-62 torch_warp(tensorInput, tensorFlow):
+ *   out[b,c,y,x] = bilinear(input[b,c], ix, iy),
+ *   gx = lin_x[x] + flow[b,0,y,x] / sx      (sx = (W-1)/2, see DSVC_FLOW_*)
+ *   ix = clamp(((gx + 1) / 2) * (W-1), 0, W-1)            (same for y)
+ * lin_x[W], lin_y[H]: the reference's torch.linspace(-1,1,W|H) base grids
+ * (modules.py:47-50), passed in so that the CPU-computed table is reproduced
+ * bit for bit.  flow is always NCHW [B,2,H,W] (ch0 = dx, ch1 = dy, pixels).
+ * input/out: [B,C,H,W] in `layout`. */
+int dsvc_warp_fwd_f32(const float* input, const float* flow, float* out,
+                      int B, int C, int H, int W,
+                      const float* lin_x, const float* lin_y,
+                      float sx, float sy, float inv_sx, float inv_sy,
+                      int flow_mode, int layout, int algo, void* stream);
+
+/* Gradient of the above (autograd of modules.py:25-62 = ATen
+ * grid_sampler_2d_backward + the division by sx/sy).
+ * grad_input [B,C,H,W] (nullable) MUST be zero-filled by the caller: taps are
+ * accumulated with atomics.  grad_flow [B,2,H,W] (nullable) is overwritten. */
+int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,
+                      float* grad_input, float* grad_flow,
+                      int B, int C, int H, int W,
+                      const float* lin_x, const float* lin_y,
+                      float sx, float sy, float inv_sx, float inv_sy,
+                      int flow_mode, int layout, void* stream);
+
+/* Number of double partial sums a gc launch over rows x inner elements writes. */
+int dsvc_reduce_slots(int64_t rows, int64_t inner);
+
+/* Fused Gaussian-conditional quantise / likelihood / bit estimate.
+ * Replaces compressai 1.2.1 GaussianConditional.forward / .quantize /
+ * .build_indexes and ops.ste_round as called from image_model.py:181,183,
+ * 237-238 and the log-sum of video_model.py:39-42.  For every element:
+ *   s      = max(scales, scale_bound)                      (LowerBound 0.11)
+ *   q      = rint(x - means)                               (half-to-even)
+ *   y_hat  = q + means                   -> y_hat   (ste_round value, :183)
+ *   o      = noise ? x + noise : y_hat   -> outputs (forward()'s first result)
+ *   v      = |o - means|
+ *   lik    = max(.5 erfc(-(.5-v)/(s sqrt2)) - .5 erfc(-(-.5-v)/(s sqrt2)), lik_bound)
+ *   symbols= (int32) q ; indexes = #{k < n_table-1 : scale_table[k] < s}
+ *   bits_partials[cta] = sum over the CTA's elements of ln(lik)   (double)
+ * Any output pointer may be NULL.  means may be NULL (treated as 0).
+ * noise != NULL selects training ("noise") mode for outputs/likelihood.
+ * Inputs are `rows` rows of `inner` contiguous floats with per-tensor row strides
+ * (*_rs, in elements): this is exactly the memory shape of the reference's
+ * y.chunk(num_slices, 1) slices for batch > 1 (image_model.py:164).  A dense
+ * tensor is rows = 1, inner = numel.  Outputs are dense [rows, inner]. */
+int dsvc_gc_fwd_f32(const float* x, const float* scales, const float* means,
+                    const float* noise,
+                    float* outputs, float* likelihood, float* y_hat,
+                    int32_t* symbols, int32_t* indexes,
+                    const float* scale_table, int n_table,
+                    double* bits_partials,
+                    float scale_bound, float lik_bound,
+                    int64_t rows, int64_t inner,
+                    int64_t x_rs, int64_t scales_rs, int64_t means_rs, int64_t noise_rs,
+                    void* stream);
+
+/* Gradient of the likelihood branch of the above (autograd of
+ * GaussianConditional._likelihood + the two LowerBound rules,
+ * backward pass-through if (x >= bound) or (grad < 0)).
+ * grad_lik: dL/d likelihood.  Outputs (nullable): grad_x (= -grad_means in
+ * noise mode, zero in round mode), grad_scales, grad_means. */
+int dsvc_gc_bwd_f32(const float* grad_lik, const float* x, const float* scales,
+                    const float* means, const float* noise,
+                    float* grad_x, float* grad_scales, float* grad_means,
+                    float scale_bound, float lik_bound,
+                    int64_t rows, int64_t inner,
+                    int64_t x_rs, int64_t scales_rs, int64_t means_rs, int64_t noise_rs,
+                    void* stream);
+
+/* Number of packed floats per channel expected by dsvc_eb_*: softplus'd
+ * matrices, biases, tanh'd factors of the 1-3-3-3-3-1 network, then the
+ * median; see deepsvc_b200/entropy.py::pack_bottleneck_params. */
+#define DSVC_EB_PARAMS_PER_CHANNEL 60
+
+/* Fused factorised-prior quantise / likelihood / bit estimate on z [B,C,S]
+ * (S = h*w, NCHW).  Replaces compressai 1.2.1 EntropyBottleneck.forward
+ * (call site image_model.py:155) and the z part of image_model.py:160-162:
+ *   o   = noise ? z + noise : rint(z - med_c) + med_c
+ *   L,U = logits_cumulative_c(o -/+ .5) ; sg = -sign(L+U)
+ *   lik = max(|sigmoid(sg U) - sigmoid(sg L)|, lik_bound)
+ * outputs <- o, z_hat <- rint(z - med)+med (always), likelihood, bits partials
+ * (sum of ln lik per CTA).  Any output may be NULL. */
+int dsvc_eb_fwd_f32(const float* z, const float* noise, const float* params,
+                    float* outputs, float* likelihood, float* z_hat,
+                    double* bits_partials, float lik_bound,
+                    int B, int C, int S, void* stream);
+int dsvc_eb_reduce_slots(int B, int C, int S);
+
+/* Gradient of the likelihood branch of dsvc_eb_fwd_f32: grad_z [B,C,S]
+ * (zero in round mode) and grad_params [C,DSVC_EB_PARAMS_PER_CHANNEL] w.r.t. the
+ * PACKED (already softplus'd / tanh'd) parameters; must be zero-filled by the
+ * caller (accumulated with atomics).  Either may be NULL. */
+int dsvc_eb_bwd_f32(const float* grad_lik, const float* z, const float* noise,
+                    const float* params, float* grad_z, float* grad_params,
+                    float lik_bound, int B, int C, int S, void* stream);
+
+/* out[i] = scale[i] * sum(partials[seg_offsets[i] .. seg_offsets[i+1])), fixed
+ * summation order, fp64.  With scale = -1/(ln2 * pixels) this is the bpp of
+ * video_model.py:39-42.  seg_offsets is a DEVICE int32 array [nseg+1]. */
+int dsvc_bits_finalize_f64(const double* partials, const int32_t* seg_offsets,
+                           const double* scales, double* out, int nseg, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSVC_B200_H_ */

@@ -1,0 +1,118 @@
+"""End-to-end P-frame hot path on the GPU vs the CPU oracle, eager and graph-replayed,
+plus the drop-in installation into reference-shaped code."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 256, 448), (2, 128, 128)])
+def test_pframe_vs_oracle_and_graph(oracle, B, H, W):
+    import deepsvc_b200 as dsvc
+    from deepsvc_b200 import synthetic, _lib
+    from deepsvc_b200.hotpath import PFrameHotPath
+    dev = torch.device("cuda:0")
+    cpu_in = synthetic.make_pframe_inputs(B=B, H=H, W=W, seed=16)
+    mc, mg = {}, {}
+    for name, ch in (("mv", 64), ("res", 96)):
+        eb_o, gc_o = oracle.make_entropy_models(ch, seed=ch)
+        eb = dsvc.EntropyBottleneck(ch)
+        eb.load_state_dict(eb_o.state_dict(), strict=False)
+        mc[name] = (eb_o.eval(), gc_o.eval())
+        mg[name] = (eb.to(dev).eval(), dsvc.GaussianConditional(None).to(dev).eval())
+    with torch.no_grad():
+        ref = oracle.pframe_hotpath(cpu_in, mc)
+    hp = PFrameHotPath(synthetic.to_device(cpu_in, dev), mg, flow_mode=_lib.FLOW_TRUE_DIVIDE)
+    assert hp.n_launches == 25
+    hp.run()
+    torch.cuda.synchronize()
+    got = hp.results()
+
+    def check(got):
+        for a, b in zip(got["spynet"] + [got["warped_frame"], got["warped_feature"]],
+                        ref["spynet"] + [ref["warped_frame"], ref["warped_feature"]]):
+            err = (a.cpu() - b).abs().max().item()
+            assert err <= 1e-5 * max(1.0, b.abs().max().item())
+        for name in ("mv", "res"):
+            assert torch.equal(got[f"{name}_y_hat"].cpu(), ref[f"{name}_y_hat"])
+            assert torch.equal(got[f"{name}_z_hat"].cpu(), ref[f"{name}_z_hat"])
+            rb = float(ref[f"bpp_{name}"])
+            assert abs(got[f"bpp_{name}"] - rb) <= 1e-4 * abs(rb)
+
+    check(got)
+    first = (got["bpp_mv"], got["bpp_res"])
+    # graph replay: zero the outputs, replay, same answers bit for bit (deterministic bits)
+    hp.capture()
+    for t in hp.out["spynet"] + [hp.out["warped_frame"], hp.out["warped_feature"]]:
+        t.zero_()
+    hp.bpp.zero_()
+    hp.replay()
+    torch.cuda.synchronize()
+    got2 = hp.results()
+    check(got2)
+    assert (got2["bpp_mv"], got2["bpp_res"]) == first
+
+
+def test_dropin_on_reference_shaped_codec(oracle):
+    """A codec with the reference's call pattern (image_model.py:151-199: EB on z, 8 slice
+    GC calls fed by convs, ste_round y_hat) gives the same y_hat (bit-exact) and bpp
+    (1e-4) after swap_entropy_models() as with the oracle's entropy models on the GPU."""
+    import math
+    import deepsvc_b200 as dsvc
+    import torch.nn as nn
+    dev = torch.device("cuda:0")
+
+    class MiniCodec(nn.Module):
+        def __init__(self):
+            super().__init__()
+            N = 16
+            self.N = N
+            self.g_a = nn.Conv2d(3, N, 5, 4, 2)
+            self.h_a = nn.Conv2d(N, N, 3, 2, 1)
+            self.h_s = nn.ConvTranspose2d(N, 2 * N, 3, 2, 1, output_padding=1)
+            self.cc = nn.ModuleList(nn.Conv2d(2 * N + 2 * min(i, 4), 4, 3, 1, 1) for i in range(8))
+            self.entropy_bottleneck = oracle.EntropyBottleneck(N)
+            self.gaussian_conditional = oracle.GaussianConditional(None)
+
+        def forward(self, x, ste_round):
+            y = self.g_a(x)
+            z = self.h_a(y)
+            _, z_lik = self.entropy_bottleneck(z)
+            off = self.entropy_bottleneck._get_medians()
+            z_hat = ste_round(z - off) + off
+            hyper = self.h_s(z_hat)
+            y_hat_slices, liks = [], []
+            for i, y_slice in enumerate(y.chunk(8, 1)):
+                sup = torch.cat([hyper] + y_hat_slices[:4], 1)
+                p = self.cc[i](sup)
+                mu, scale = p[:, :2], p[:, 2:].abs() + 0.02
+                _, lik = self.gaussian_conditional(y_slice, scale.contiguous(), mu.contiguous())
+                liks.append(lik)
+                y_hat_slices.append(ste_round(y_slice - mu) + mu)
+            return torch.cat(y_hat_slices, 1), torch.cat(liks, 1), z_lik
+
+    torch.manual_seed(0)
+    m = MiniCodec().to(dev).eval()
+    x = torch.rand(2, 3, 64, 96, device=dev)
+    with torch.no_grad():
+        y_ref, l_ref, zl_ref = m(x, oracle.ste_round)
+    assert dsvc.swap_entropy_models(m) == 2
+    assert isinstance(m.gaussian_conditional, dsvc.GaussianConditional)
+    with torch.no_grad():
+        y_got, l_got, zl_got = m(x, dsvc.ste_round)
+    assert torch.equal(y_got, y_ref)
+    b_ref = (torch.log(l_ref).sum() + torch.log(zl_ref).sum()).item() / -math.log(2)
+    b_got = (torch.log(l_got).sum() + torch.log(zl_got).sum()).item() / -math.log(2)
+    assert abs(b_got - b_ref) <= 1e-4 * abs(b_ref)
+    # training mode: same noise stream as the reference (same torch generator calls)
+    m.train()
+    torch.manual_seed(5)
+    _, l_got, zl_got = m(x, dsvc.ste_round)
+    (torch.log(l_got).sum() + torch.log(zl_got).sum()).backward()
+    assert m.g_a.weight.grad is not None and torch.isfinite(m.g_a.weight.grad).all()
+    assert m.entropy_bottleneck._matrix0.grad is not None

@@ -1,0 +1,206 @@
+"""GPU parity of the warp kernels (through the C ABI) against the CPU oracle
+(= the reference's torch_warp arithmetic), the golden fixtures, and stock torch CUDA.
+
+Tolerance (north_star): warped tensors within 1e-5 relative in fp32.  Stated here as
+max|a-b| <= 1e-5 * max(1, max|ref|) plus an elementwise allclose(rtol=1e-5, atol=2e-6)
+(atol covers cancellation in the 4-tap sum; observed error is ~3e-7).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = ["gather", "auto"]
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def assert_warp_close(got, ref, what=""):
+    got = got.detach().cpu()
+    ref = ref.detach().cpu()
+    err = (got - ref).abs().max().item()
+    tol = 1e-5 * max(1.0, ref.abs().max().item())
+    assert err <= tol, f"{what}: max abs err {err:.3e} > {tol:.3e}"
+    assert torch.allclose(got, ref, rtol=1e-5, atol=2e-6), what
+
+
+def _warp(inp, flow, mode, algo):
+    import deepsvc_b200 as d
+    from deepsvc_b200 import _lib
+    fm = {"cpu": _lib.FLOW_TRUE_DIVIDE, "cuda": _lib.FLOW_MUL_RECIPROCAL}[mode]
+    al = {"gather": _lib.WARP_GATHER, "auto": _lib.WARP_AUTO, "tma": _lib.WARP_TMA}[algo]
+    return d.warp_forward(inp, flow, flow_mode=fm, algo=al)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "warp_*.npz"))))
+def test_golden_fixtures(path, algo):
+    """Fixtures produced by the reference's own modules.torch_warp (CPU branch)."""
+    d = np.load(path)
+    inp, flow = torch.from_numpy(d["input"]).to(_dev()), torch.from_numpy(d["flow"]).to(_dev())
+    assert_warp_close(_warp(inp, flow, "cpu", algo), torch.from_numpy(d["out"]), os.path.basename(path))
+
+
+SHAPES = [  # (B, C, H, W): the six per-frame shapes of config 1 + ragged / batched cases
+    (1, 3, 32, 56), (1, 3, 64, 112), (1, 3, 128, 224), (1, 3, 256, 448), (1, 64, 256, 448),
+    (8, 3, 32, 32), (8, 64, 64, 64), (2, 5, 17, 23), (1, 1, 2, 7), (1, 2, 9, 2), (3, 7, 33, 130),  # (H or W == 1 is NaN in the reference itself: 0/0)
+]
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("kind", ["smooth", "stress", "border"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_vs_cpu_oracle(oracle, shape, kind, algo):
+    from deepsvc_b200 import synthetic
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) * 7 + len(kind))
+    inp = torch.randn(B, C, H, W, generator=g)
+    if kind == "smooth":
+        flow = synthetic.smooth_flow(B, H, W, g)
+    elif kind == "stress":
+        flow = synthetic.stress_flow(B, H, W, g)
+    else:
+        flow = synthetic.border_flow(B, H, W, g, margin=max(1, min(H, W) // 4), reach=40.0)
+    ref = oracle.torch_warp(inp, flow)
+    got = _warp(inp.to(_dev()), flow.to(_dev()), "cpu", algo)
+    assert_warp_close(got, ref, f"{shape} {kind} {algo}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("shape", [(1, 3, 256, 448), (2, 64, 128, 192), (1, 5, 31, 47)])
+def test_vs_stock_torch_cuda(oracle, shape, algo):
+    """The reference's CUDA branch (modules.py:44-62) run with stock torch on this GPU."""
+    from deepsvc_b200 import synthetic
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    inp = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow = synthetic.smooth_flow(B, H, W, g, sigma=8.0).to(_dev())
+    ref = oracle.torch_warp(inp, flow)  # same restatement, tensors on the GPU
+    got = _warp(inp, flow, "cuda", algo)
+    assert_warp_close(got, ref, f"{shape} cuda-branch {algo}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_exact_properties(algo):
+    g = torch.Generator().manual_seed(3)
+    inp = torch.randn(2, 6, 40, 72, generator=g).to(_dev())
+    zero = torch.zeros(2, 2, 40, 72, device=_dev())
+    out = _warp(inp, zero, "cuda", algo)
+    assert (out - inp).abs().max().item() <= 2e-4  # identity up to (g+1)/2*(W-1) rounding
+    # linearity in the input: warp(a*x + y) == a*warp(x) + warp(y) within fp32 rounding
+    flow = (torch.randn(2, 2, 40, 72, generator=g) * 3).to(_dev())
+    x, y = inp, torch.randn(2, 6, 40, 72, generator=g).to(_dev())
+    lhs = _warp(2.0 * x + y, flow, "cuda", algo)
+    rhs = 2.0 * _warp(x, flow, "cuda", algo) + _warp(y, flow, "cuda", algo)
+    assert torch.allclose(lhs, rhs, rtol=1e-5, atol=1e-5)
+    # a constant image stays constant under any flow (weights sum to 1)
+    c = torch.full((1, 3, 24, 40), 0.75, device=_dev())
+    fl = (torch.randn(1, 2, 24, 40, generator=g) * 50).to(_dev())
+    assert (_warp(c, fl, "cuda", algo) - 0.75).abs().max().item() <= 1e-6
+    # far outside -> border value
+    fl = torch.zeros(1, 2, 24, 40, device=_dev())
+    fl[:, 0] = 1e4
+    img = torch.randn(1, 3, 24, 40, generator=g).to(_dev())
+    out = _warp(img, fl, "cuda", algo)
+    assert (out - img[:, :, :, -1:].expand(-1, -1, -1, 40)).abs().max().item() <= 1e-4
+
+
+def test_gather_and_auto_agree_bitwise():
+    from deepsvc_b200 import synthetic
+    g = torch.Generator().manual_seed(11)
+    inp = torch.randn(1, 64, 128, 256, generator=g).to(_dev())
+    flow = synthetic.smooth_flow(1, 128, 256, g).to(_dev())
+    assert torch.equal(_warp(inp, flow, "cuda", "gather"), _warp(inp, flow, "cuda", "auto"))
+
+
+def test_channels_last(oracle):
+    from deepsvc_b200 import synthetic
+    import deepsvc_b200 as d
+    g = torch.Generator().manual_seed(5)
+    inp = torch.randn(2, 64, 48, 80, generator=g)
+    flow = synthetic.smooth_flow(2, 48, 80, g)
+    ref = oracle.torch_warp(inp, flow)
+    x = inp.to(_dev()).contiguous(memory_format=torch.channels_last)
+    d.set_flow_arithmetic("cpu")
+    try:
+        out = d.torch_warp(x, flow.to(_dev()))
+    finally:
+        d.set_flow_arithmetic("cuda")
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    assert_warp_close(out, ref, "nhwc")
+    bad = torch.randn(1, 3, 8, 8).to(_dev()).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError, match="layout"):
+        d.torch_warp(bad[:, :, ::2], torch.zeros(1, 2, 4, 8, device=_dev()))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "warp_*.npz"))))
+def test_backward_golden(path):
+    """grad_input / grad_flow against autograd of the reference function (fixtures)."""
+    import deepsvc_b200 as d
+    g = np.load(path)
+    inp = torch.from_numpy(g["input"]).to(_dev()).requires_grad_(True)
+    flow = torch.from_numpy(g["flow"]).to(_dev()).requires_grad_(True)
+    d.set_flow_arithmetic("cpu")
+    try:
+        out = d.torch_warp(inp, flow)
+        gin, gflow = torch.autograd.grad(out, (inp, flow), torch.from_numpy(g["grad_out"]).to(_dev()))
+    finally:
+        d.set_flow_arithmetic("cuda")
+    # gradients: 1e-4 relative to the tensor's scale (atomics reorder the fp32 sums)
+    for got, ref, nm in ((gin, g["grad_input"], "grad_input"), (gflow, g["grad_flow"], "grad_flow")):
+        ref = torch.from_numpy(ref)
+        err = (got.cpu() - ref).abs().max().item()
+        assert err <= 1e-4 * max(1.0, ref.abs().max().item()), f"{nm} {err}"
+
+
+@pytest.mark.parametrize("need", [(True, True), (False, True), (True, False)])
+def test_backward_vs_stock_torch_cuda(oracle, need):
+    import deepsvc_b200 as d
+    from deepsvc_b200 import synthetic
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W = 2, 16, 40, 56
+    inp0 = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow0 = synthetic.smooth_flow(B, H, W, g, sigma=6.0).to(_dev())
+    # push some samples onto / past the border: gradient must vanish there
+    flow0[:, 0, :, :3] = -10.0
+    gout = torch.randn(B, C, H, W, generator=g).to(_dev())
+    res = []
+    for fn in (oracle.torch_warp, d.torch_warp):
+        inp = inp0.clone().requires_grad_(need[0])
+        flow = flow0.clone().requires_grad_(need[1])
+        out = fn(inp, flow)
+        out.backward(gout)
+        res.append((inp.grad, flow.grad))
+    for a, b, nm in zip(res[1], res[0], ("grad_input", "grad_flow")):
+        if b is None:
+            assert a is None
+            continue
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{nm} {err}"
+    if need[1]:
+        assert res[1][1][:, 0, :, :3].abs().max().item() == 0.0
+
+
+def test_full_size_1080p_properties():
+    """BASELINE config 2 size (1088x1920, 64 ch): size-independent checks -- an integer
+    shift is reproduced exactly in the interior, and the op is idempotent under zero
+    flow up to coordinate rounding."""
+    dev = _dev()
+    g = torch.Generator().manual_seed(2)
+    inp = torch.randn(1, 64, 1088, 1920, generator=g).to(dev)
+    flow = torch.zeros(1, 2, 1088, 1920, device=dev)
+    flow[:, 0] = 5.0
+    flow[:, 1] = -3.0
+    import deepsvc_b200 as d
+    out = d.torch_warp(inp, flow)
+    ref = inp[:, :, :-3, 5:]
+    got = out[:, :, 3:, :-5]
+    assert (got - ref).abs().max().item() <= 5e-3  # coordinate rounding ~2e-4 px * gradient
+    # checksum property: sum over taps of weights is 1 -> mean preserved for a shift
+    assert abs(got.double().mean().item() - ref.double().mean().item()) < 1e-5
