@@ -111,6 +111,39 @@ def test_exact_properties(algo):
     assert (out - img[:, :, :, -1:].expand(-1, -1, -1, 40)).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("kind", ["smooth", "stress", "border"])
+@pytest.mark.parametrize("shape", [(2, 5, 40, 72), (1, 3, 32, 64), (1, 16, 100, 132), (3, 7, 33, 128),
+                                   (1, 8, 8, 4), (2, 9, 65, 260)])
+def test_tma_forced(oracle, shape, kind):
+    """The TMA-staged kernel on shapes the auto policy would not pick: odd channel
+    counts (partial last channel group), batch > 1 (plane index crosses items), partial
+    edge tiles, and wild flows (per-tile in-kernel fallback)."""
+    from deepsvc_b200 import synthetic
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape) * 3 + len(kind))
+    inp = torch.randn(B, C, H, W, generator=g)
+    if kind == "smooth":
+        flow = synthetic.smooth_flow(B, H, W, g)
+    elif kind == "stress":
+        flow = synthetic.stress_flow(B, H, W, g)
+    else:
+        flow = synthetic.border_flow(B, H, W, g, margin=max(1, min(H, W) // 4), reach=40.0)
+    ref = oracle.torch_warp(inp, flow)
+    got = _warp(inp.to(_dev()), flow.to(_dev()), "cpu", "tma")
+    assert_warp_close(got, ref, f"{shape} {kind} tma")
+    assert torch.equal(got, _warp(inp.to(_dev()), flow.to(_dev()), "cpu", "gather"))
+
+
+def test_tma_rejects_unaligned_rows():
+    import deepsvc_b200 as d
+    from deepsvc_b200 import _lib
+    x = torch.randn(1, 8, 16, 30, device=_dev())  # W % 4 != 0: TMA needs 16-byte rows
+    fl = torch.zeros(1, 2, 16, 30, device=_dev())
+    with pytest.raises(_lib.DeepSVCNativeError):
+        d.warp_forward(x, fl, algo=_lib.WARP_TMA)
+    d.warp_forward(x, fl, algo=_lib.WARP_AUTO)  # auto falls back to the gather kernel
+
+
 def test_gather_and_auto_agree_bitwise():
     from deepsvc_b200 import synthetic
     g = torch.Generator().manual_seed(11)
