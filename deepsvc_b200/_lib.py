@@ -25,7 +25,9 @@ SIGNATURES = {
     "dsvc_error_string": (c_char_p, [c_int]),
     "dsvc_device_arch": (c_int, []),
     "dsvc_warp_fwd_f32": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
-                                  c_float, c_float, c_float, c_float, c_int, c_int, c_int, _P]),
+                                  c_float, c_float, c_float, c_float, c_int, c_int, c_int,
+                                  _P, c_size_t, _P]),
+    "dsvc_warp_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dsvc_warp_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                   c_float, c_float, c_float, c_float, c_int, c_int, _P]),
     "dsvc_reduce_slots": (c_int, [c_int64, c_int64]),
@@ -38,6 +40,16 @@ SIGNATURES = {
     "dsvc_eb_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
     "dsvc_eb_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
     "dsvc_bits_finalize_f64": (c_int, [_P, _P, _P, _P, c_int, _P]),
+    # host-side range coder / CDF quantiser
+    "dsvc_pmf_to_quantized_cdf_host": (c_int, [_P, c_int, c_int, _P]),
+    "dsvc_rans_encoder_create": (c_void_p, []),
+    "dsvc_rans_encoder_destroy": (None, [_P]),
+    "dsvc_rans_encoder_push": (c_int, [_P, _P, _P, c_int64, _P, c_int, c_int, _P, _P]),
+    "dsvc_rans_encoder_bound": (c_int64, [_P]),
+    "dsvc_rans_encoder_flush": (c_int, [_P, _P, c_int64, _P]),
+    "dsvc_rans_decoder_create": (c_void_p, [_P, c_int64]),
+    "dsvc_rans_decoder_destroy": (None, [_P]),
+    "dsvc_rans_decoder_decode": (c_int, [_P, _P, c_int64, _P, c_int, c_int, _P, _P, _P]),
 }
 
 _lib = None

@@ -54,4 +54,65 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
     return t;
 }
 
+// One thread: output pixel (x, y) of batch item b, channels [c0, cend) -- the direct
+// read-only-path gather (used by the gather kernel and by the deferred-tile kernel).
+template <int UNROLL>
+__device__ __forceinline__ void gather_pixel(const float* __restrict__ in,
+                                             const float* __restrict__ flow,
+                                             float* __restrict__ out,
+                                             const float* __restrict__ lin_x,
+                                             const float* __restrict__ lin_y, const WarpParams& p,
+                                             int b, int x, int y, int c0, int cend) {
+    const size_t plane = (size_t)p.H * p.W;
+    const size_t pix = (size_t)y * p.W + x;
+    const float* fl = flow + (size_t)b * 2 * plane + pix;
+    const float fx = __ldg(fl), fy = __ldg(fl + plane);
+    const float ix = source_coord(__ldg(lin_x + x), fx, p.sx, p.inv_sx, p.flow_mode, p.W);
+    const float iy = source_coord(__ldg(lin_y + y), fy, p.sy, p.inv_sy, p.flow_mode, p.H);
+    const Taps t = make_taps(ix, iy, p.W, p.H);
+    const int o_nw = t.y0 * p.W + t.x0;
+    const int dx = t.x1ok ? 1 : 0;    // clamped so that the address stays legal;
+    const int dy = t.y1ok ? p.W : 0;  // the value is discarded when the tap is outside
+    const float* ip = in + ((size_t)b * p.C + c0) * plane + o_nw;
+    float* op = out + ((size_t)b * p.C + c0) * plane + pix;
+    int c = c0;
+    for (; c + UNROLL <= cend; c += UNROLL) {
+        float v[UNROLL][4];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const float* q = ip + (size_t)u * plane;
+            v[u][0] = __ldg(q);
+            v[u][1] = __ldg(q + dx);
+            v[u][2] = __ldg(q + dy);
+            v[u][3] = __ldg(q + dy + dx);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float acc = __fmul_rn(v[u][0], t.nw);
+            acc = t.x1ok ? fmaf(v[u][1], t.ne, acc) : acc;
+            acc = t.y1ok ? fmaf(v[u][2], t.sw, acc) : acc;
+            acc = (t.x1ok && t.y1ok) ? fmaf(v[u][3], t.se, acc) : acc;
+            st_stream1(op + (size_t)u * plane, acc);
+        }
+        ip += (size_t)UNROLL * plane;
+        op += (size_t)UNROLL * plane;
+    }
+    for (; c < cend; ++c) {
+        float acc = __fmul_rn(__ldg(ip), t.nw);
+        acc = t.x1ok ? fmaf(__ldg(ip + dx), t.ne, acc) : acc;
+        acc = t.y1ok ? fmaf(__ldg(ip + dy), t.sw, acc) : acc;
+        acc = (t.x1ok && t.y1ok) ? fmaf(__ldg(ip + dy + dx), t.se, acc) : acc;
+        st_stream1(op, acc);
+        ip += plane;
+        op += plane;
+    }
+}
+
+// Work list of tiles the staged kernel could not stage (bounding box too large).
+struct DeferredTiles {
+    int count;
+    int pad[3];
+    int tiles[1];  // linear tile ids: (b * tiles_y + ty) * tiles_x + tx
+};
+
 }  // namespace dsvc

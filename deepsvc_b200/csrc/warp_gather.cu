@@ -24,49 +24,36 @@ warp_fwd_nchw_gather(const float* __restrict__ in, const float* __restrict__ flo
     const int b = blockIdx.z / nchunk;
     const int c0 = (blockIdx.z - b * nchunk) * cpc;
     if (x >= p.W || y >= p.H) return;
-    const size_t plane = (size_t)p.H * p.W;
-    const size_t pix = (size_t)y * p.W + x;
-    const float* fl = flow + (size_t)b * 2 * plane + pix;
-    const float fx = __ldg(fl), fy = __ldg(fl + plane);
-    const float ix = source_coord(__ldg(lin_x + x), fx, p.sx, p.inv_sx, p.flow_mode, p.W);
-    const float iy = source_coord(__ldg(lin_y + y), fy, p.sy, p.inv_sy, p.flow_mode, p.H);
-    const Taps t = make_taps(ix, iy, p.W, p.H);
-    const int o_nw = t.y0 * p.W + t.x0;
-    const int dx = t.x1ok ? 1 : 0;         // clamped so that the address stays legal;
-    const int dy = t.y1ok ? p.W : 0;       // the value is discarded when the tap is outside
-    const int cend = min(p.C, c0 + cpc);
-    const float* ip = in + ((size_t)b * p.C + c0) * plane + o_nw;
-    float* op = out + ((size_t)b * p.C + c0) * plane + pix;
-    int c = c0;
-    for (; c + UNROLL <= cend; c += UNROLL) {
-        float v[UNROLL][4];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const float* q = ip + (size_t)u * plane;
-            v[u][0] = __ldg(q);
-            v[u][1] = __ldg(q + dx);
-            v[u][2] = __ldg(q + dy);
-            v[u][3] = __ldg(q + dy + dx);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            float acc = __fmul_rn(v[u][0], t.nw);
-            acc = t.x1ok ? fmaf(v[u][1], t.ne, acc) : acc;
-            acc = t.y1ok ? fmaf(v[u][2], t.sw, acc) : acc;
-            acc = (t.x1ok && t.y1ok) ? fmaf(v[u][3], t.se, acc) : acc;
-            st_stream1(op + (size_t)u * plane, acc);
-        }
-        ip += (size_t)UNROLL * plane;
-        op += (size_t)UNROLL * plane;
-    }
-    for (; c < cend; ++c) {
-        float acc = __fmul_rn(__ldg(ip), t.nw);
-        acc = t.x1ok ? fmaf(__ldg(ip + dx), t.ne, acc) : acc;
-        acc = t.y1ok ? fmaf(__ldg(ip + dy), t.sw, acc) : acc;
-        acc = (t.x1ok && t.y1ok) ? fmaf(__ldg(ip + dy + dx), t.se, acc) : acc;
-        st_stream1(op, acc);
-        ip += plane;
-        op += plane;
+    gather_pixel<UNROLL>(in, flow, out, lin_x, lin_y, p, b, x, y, c0, min(p.C, c0 + cpc));
+}
+
+// Tiles deferred by the staged kernel (warp_tma.cu): a persistent grid walks the work
+// list; one work item = a 32 x 8 pixel block x 16 channels of a deferred tile, i.e. the
+// same CTA shape (and occupancy) as the gather kernel above.
+__global__ void __launch_bounds__(256)
+warp_fwd_deferred_tiles(const float* __restrict__ in, const float* __restrict__ flow,
+                        float* __restrict__ out, const float* __restrict__ lin_x,
+                        const float* __restrict__ lin_y, WarpParams p,
+                        const DeferredTiles* __restrict__ list, int tile_w, int tile_h,
+                        int tiles_x, int tiles_y) {
+    const int count = list->count;
+    if (count == 0) return;
+    constexpr int CPC = 16;
+    const int nchunk = (p.C + CPC - 1) / CPC;
+    const int bx = tile_w / 32, by = tile_h / 8;
+    const int per_tile = bx * by * nchunk;
+    const long long total = (long long)count * per_tile;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const int t = list->tiles[w / per_tile];
+        int r = (int)(w % per_tile);
+        const int chunk = r % nchunk; r /= nchunk;
+        const int sx = r % bx, sy = r / bx;
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+        const int x = tx * tile_w + sx * 32 + threadIdx.x;
+        const int y = ty * tile_h + sy * 8 + threadIdx.y;
+        if (x < p.W && y < p.H)
+            gather_pixel<4>(in, flow, out, lin_x, lin_y, p, b, x, y, chunk * CPC,
+                            min(p.C, chunk * CPC + CPC));
     }
 }
 
@@ -201,9 +188,21 @@ warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
 
 using namespace dsvc;
 
+int dsvc_warp_deferred_launch(const float* input, const float* flow, float* out,
+                              const float* lin_x, const float* lin_y, const WarpParams& p,
+                              const DeferredTiles* list, int tile_w, int tile_h, int tiles_x,
+                              int tiles_y, cudaStream_t st) {
+    dim3 block(32, 8);
+    warp_fwd_deferred_tiles<<<DSVC_NUM_SMS * 8, block, 0, st>>>(input, flow, out, lin_x, lin_y, p,
+                                                               list, tile_w, tile_h, tiles_x,
+                                                               tiles_y);
+    return (int)cudaGetLastError();
+}
+
 int dsvc_warp_fwd_tma_launch(const float* input, const float* flow, float* out,
                              const float* lin_x, const float* lin_y, const WarpParams& p,
-                             bool force, cudaStream_t st);  // warp_tma.cu
+                             bool force, void* workspace, size_t workspace_bytes,
+                             cudaStream_t st);  // warp_tma.cu
 
 static int warp_args_ok(const void* a, const void* b, const void* c, int B, int C, int H, int W,
                         const void* lx, const void* ly) {
@@ -214,7 +213,8 @@ static int warp_args_ok(const void* a, const void* b, const void* c, int B, int 
 extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* out, int B, int C,
                                  int H, int W, const float* lin_x, const float* lin_y, float sx,
                                  float sy, float inv_sx, float inv_sy, int flow_mode, int layout,
-                                 int algo, void* stream) {
+                                 int algo, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
     DSVC_CHECK_ARG(warp_args_ok(input, flow, out, B, C, H, W, lin_x, lin_y));
     DSVC_CHECK_ARG(flow_mode == 0 || flow_mode == 1);
     cudaStream_t st = (cudaStream_t)stream;
@@ -237,7 +237,7 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
     DSVC_CHECK_ARG(layout == DSVC_LAYOUT_NCHW);
     if (algo == DSVC_WARP_AUTO || algo == DSVC_WARP_TMA) {
         const int r = dsvc_warp_fwd_tma_launch(input, flow, out, lin_x, lin_y, p,
-                                               algo == DSVC_WARP_TMA, st);
+                                               algo == DSVC_WARP_TMA, workspace, workspace_bytes, st);
         if (r != -1) return r;  // -1: shape not supported by the staged kernel -> gather
         if (algo == DSVC_WARP_TMA) return (int)cudaErrorInvalidValue;
     }
@@ -252,6 +252,13 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
     else
         warp_fwd_nchw_gather<1><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
     DSVC_RETURN_LAST();
+}
+
+extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    // deferred-tile list: header + one int per tile of the smallest staged tile (32 x 16)
+    const size_t ntiles = (size_t)B * ((W + 31) / 32) * ((H + 15) / 16);
+    return sizeof(DeferredTiles) + ntiles * sizeof(int) + 16;
 }
 
 extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,

@@ -7,9 +7,11 @@
 //   1. the 8 consumer warps compute every pixel's source coordinate (reference
 //      arithmetic, warp_common.cuh) and the tile's source bounding box;
 //   2. a producer warp streams that box, CC channel planes at a time, from HBM/L2 into
-//      a STAGES-deep shared-memory ring with 3-D TMA loads
-//      (cp.async.bulk.tensor.3d, box = BW x 8 rows x CC planes, as many 8-row boxes as
-//      the bounding box is tall), signalling mbarriers with complete_tx;
+//      a STAGES-deep shared-memory ring with 3-D TMA loads (cp.async.bulk.tensor.3d over
+//      the tensor viewed as (x, plane, y): box = BW x CC planes x 8 rows, as many 8-row
+//      boxes as the bounding box is tall), signalling mbarriers with complete_tx.  The
+//      (x, plane, y) order makes the shared-memory row pitch CC*BW floats = a multiple
+//      of 32 banks, so lanes that sample different source rows never bank-conflict;
 //   3. the consumers gather the four taps of each of their 8 pixels from shared memory
 //      (no tag lookup, no 128-byte-line split: one wavefront per conflict-free LDS
 //      instead of two L1 wavefronts per unaligned global gather) and store coalesced
@@ -17,6 +19,9 @@
 // Coordinates and weights are computed once per pixel and reused for all C channels.
 // A tile whose bounding box does not fit the staging box (wild flow) falls back to the
 // read-only-path gather inside the same kernel, so results never depend on the path.
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -60,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: protocol bug, do not hang
     }
 }
 __device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y,
@@ -70,6 +75,23 @@ __device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* tmap,
         "[%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
+}
+
+template <class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+// compile-time loop: the index is usable as a template argument (immediate offsets)
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+template <int IMM>
+__device__ __forceinline__ float lds_imm(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(IMM));
+    return v;
 }
 
 }  // namespace tma
@@ -83,11 +105,13 @@ struct TmaCfg {
     static constexpr int XH = TW / 32;                         // 32-pixel column groups
     static constexpr int PPT = ROWS_PER_WARP * XH;             // pixels per thread
     static constexpr int ROWCHUNK = 8;                         // rows per TMA box
-    static constexpr int CHUNK_FLOATS = CC * ROWCHUNK * BW;    // one TMA box
+    static constexpr int ROW_PITCH = CC * BW;                  // smem floats between box rows
+    static constexpr int CHUNK_FLOATS = CC * ROWCHUNK * BW;    // one TMA box [8 rows][CC][BW]
     static constexpr int STAGE_FLOATS = (BHMAX / ROWCHUNK) * CHUNK_FLOATS;
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * sizeof(float);
     static_assert(TH % CONSUMER_WARPS == 0 && TW % 32 == 0 && BHMAX % ROWCHUNK == 0, "tile shape");
     static_assert((BW * 4) % 16 == 0 && (CHUNK_FLOATS * 4) % 128 == 0, "TMA alignment");
+    static_assert(ROW_PITCH % 32 == 0, "row pitch must be a multiple of the 32 banks");
 };
 
 struct PixelTaps {
@@ -101,7 +125,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2)
 warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in,
                     const float* __restrict__ flow, float* __restrict__ out,
                     const float* __restrict__ lin_x, const float* __restrict__ lin_y,
-                    WarpParams p) {
+                    WarpParams p, DeferredTiles* __restrict__ deferred) {
     constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, CC = Cfg::CC, STAGES = Cfg::STAGES;
     constexpr int RPW = Cfg::ROWS_PER_WARP, XH = Cfg::XH, PPT = Cfg::PPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -171,8 +195,10 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
         mny = min(mny, s_red[w][2]); mxy = max(mxy, s_red[w][3]);
     }
     // taps reach x0+1 / y0+1 (clamped to the image)
-    const int bx0 = mnx, by0 = mny;
-    const int bw = min(mxx + 1, p.W - 1) - mnx + 1;
+    // TMA tiled loads need a 16-byte aligned start along the innermost dimension
+    // (probed on B200: an unaligned x coordinate raises "illegal instruction")
+    const int bx0 = mnx & ~3, by0 = mny;
+    const int bw = min(mxx + 1, p.W - 1) - bx0 + 1;
     const int bh = min(mxy + 1, p.H - 1) - mny + 1;
     const bool staged = bw <= BW && bh <= Cfg::BHMAX;  // CTA-uniform
     const int nchunks = (bh + Cfg::ROWCHUNK - 1) / Cfg::ROWCHUNK;
@@ -180,30 +206,60 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
     const int plane0 = b * p.C;
 
     if (!staged) {
-        // ---- fallback: direct gather of this tile (identical arithmetic)
+        // ---- fallback: direct gather of this tile (identical arithmetic).  Channel-outer
+        // loop so that all PPT pixels' taps (4*PPT independent loads) are in flight at once:
+        // a fallback CTA must not take much longer than a staged one, or it becomes the
+        // kernel's tail.
+        if (deferred != nullptr) {
+            // hand the tile to the deferred-tile kernel (full-occupancy gather) instead of
+            // letting one slow CTA become the tail of this launch
+            if (threadIdx.x == 0) {
+                const int slot = atomicAdd(&deferred->count, 1);
+                deferred->tiles[slot] = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            }
+            return;
+        }
         if (is_producer) return;
+        float w4[PPT][4];
+        int o_nw[PPT], ddx[PPT], ddy[PPT];
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
+        for (int k = 0; k < PPT; ++k) {
+            const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
+            w4[k][0] = t.nw;
+            w4[k][1] = t.x1ok ? t.ne : 0.0f;
+            w4[k][2] = t.y1ok ? t.sw : 0.0f;
+            w4[k][3] = (t.x1ok && t.y1ok) ? t.se : 0.0f;
+            o_nw[k] = valid[k] ? t.y0 * p.W + t.x0 : 0;
+            ddx[k] = (valid[k] && t.x1ok) ? 1 : 0;
+            ddy[k] = (valid[k] && t.y1ok) ? p.W : 0;
+        }
+        const float* ip = in + (size_t)plane0 * plane;
+        float* op = out + (size_t)plane0 * plane + (size_t)(ty0 + warp * RPW) * p.W + tx0 + lane;
+        constexpr int KB = PPT < 4 ? PPT : 4;  // pixels per load batch (register budget)
+        for (int c = 0; c < p.C; ++c) {
 #pragma unroll
-            for (int h = 0; h < XH; ++h) {
-                const int k = r * XH + h;
-                if (!valid[k]) continue;
-                const int x = tx0 + h * 32 + lane, y = ty0 + warp * RPW + r;
-                const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
-                const int dx = t.x1ok ? 1 : 0, dy = t.y1ok ? p.W : 0;
-                const float* ip = in + (size_t)plane0 * plane + (size_t)t.y0 * p.W + t.x0;
-                float* op = out + (size_t)plane0 * plane + (size_t)y * p.W + x;
-#pragma unroll 4
-                for (int c = 0; c < p.C; ++c) {
-                    float acc = __fmul_rn(__ldg(ip), t.nw);
-                    acc = t.x1ok ? fmaf(__ldg(ip + dx), t.ne, acc) : acc;
-                    acc = t.y1ok ? fmaf(__ldg(ip + dy), t.sw, acc) : acc;
-                    acc = (t.x1ok && t.y1ok) ? fmaf(__ldg(ip + dy + dx), t.se, acc) : acc;
-                    st_stream1(op, acc);
-                    ip += plane;
-                    op += plane;
+            for (int k0 = 0; k0 < PPT; k0 += KB) {
+                float v[KB][4];
+#pragma unroll
+                for (int j = 0; j < KB; ++j) {
+                    const float* q = ip + o_nw[k0 + j];
+                    v[j][0] = __ldg(q);
+                    v[j][1] = __ldg(q + ddx[k0 + j]);
+                    v[j][2] = __ldg(q + ddy[k0 + j]);
+                    v[j][3] = __ldg(q + ddy[k0 + j] + ddx[k0 + j]);
+                }
+#pragma unroll
+                for (int j = 0; j < KB; ++j) {
+                    const int k = k0 + j;
+                    float acc = __fmul_rn(v[j][0], w4[k][0]);
+                    acc = fmaf(v[j][1], w4[k][1], acc);
+                    acc = fmaf(v[j][2], w4[k][2], acc);
+                    acc = fmaf(v[j][3], w4[k][3], acc);
+                    if (valid[k]) st_stream1(op + (size_t)(k / XH) * p.W + (k % XH) * 32, acc);
                 }
             }
+            ip += plane;
+            op += plane;
         }
         return;
     }
@@ -218,22 +274,83 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
                 tma::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
                 float* dst = stage_buf + (size_t)s * Cfg::STAGE_FLOATS;
                 for (int k = 0; k < nchunks; ++k)
-                    tma::load_3d(dst + (size_t)k * Cfg::CHUNK_FLOATS, &tmap, bx0,
-                                 by0 + k * Cfg::ROWCHUNK, plane0 + g * CC, &full_bar[s]);
+                    tma::load_3d(dst + (size_t)k * Cfg::CHUNK_FLOATS, &tmap, bx0, plane0 + g * CC,
+                                 by0 + k * Cfg::ROWCHUNK, &full_bar[s]);
             }
         }
         return;
     }
 
-    // ---- phase 3 (consumers): gather from the staged box, store coalesced rows
+    // ---- phase 3 (consumers): gather from the staged box, store coalesced rows.
+    // Shared-memory element (row ry, channel c, column rx) of a stage lives at
+    //   (ry >> 3) * CHUNK_FLOATS + (ry & 7) * ROW_PITCH + c * BW + rx.
+    const bool fast = (tx0 + TW <= p.W) && (ty0 + TH <= p.H) && (mxx + 1 < p.W);  // CTA-uniform
+    float* obase = out + (size_t)plane0 * plane + (size_t)(ty0 + warp * RPW) * p.W + tx0 + lane;
+    if (fast) {
+        // interior tile, every east tap inside the image: byte addresses, immediate offsets
+        float wnw[PPT], wne[PPT], wsw[PPT], wse[PPT];
+        uint32_t a_n[PPT], a_s[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
+            const int rx = t.x0 - bx0, ry = t.y0 - by0;
+            const int ry1 = ry + (t.y1ok ? 1 : 0);
+            a_n[k] = 4u * (uint32_t)((ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * Cfg::ROW_PITCH + rx);
+            a_s[k] = 4u * (uint32_t)((ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * Cfg::ROW_PITCH + rx);
+            wnw[k] = t.nw;
+            wne[k] = t.ne;
+            wsw[k] = t.y1ok ? t.sw : 0.0f;
+            wse[k] = t.y1ok ? t.se : 0.0f;
+        }
+        const uint32_t sbase0 = tma::smem_u32(stage_buf);
+        for (int g = 0; g < ngroups; ++g) {
+            const int s = g % STAGES;
+            tma::mbar_wait(&full_bar[s], (g / STAGES) & 1);
+            const uint32_t sbase = sbase0 + (uint32_t)s * (Cfg::STAGE_FLOATS * 4);
+            uint32_t tn[PPT], ts[PPT];
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) { tn[k] = a_n[k] + sbase; ts[k] = a_s[k] + sbase; }
+            tma::static_for<CC>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                const int ch = g * CC + c;
+                if (ch < p.C) {
+                    float v[PPT][4];
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        v[k][0] = tma::lds_imm<c * BW * 4>(tn[k]);
+                        v[k][1] = tma::lds_imm<c * BW * 4 + 4>(tn[k]);
+                        v[k][2] = tma::lds_imm<c * BW * 4>(ts[k]);
+                        v[k][3] = tma::lds_imm<c * BW * 4 + 4>(ts[k]);
+                    }
+                    float* oc = obase + (size_t)ch * plane;
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+                        for (int h = 0; h < XH; ++h) {
+                            const int k = r * XH + h;
+                            float acc = __fmul_rn(v[k][0], wnw[k]);
+                            acc = fmaf(v[k][1], wne[k], acc);
+                            acc = fmaf(v[k][2], wsw[k], acc);
+                            acc = fmaf(v[k][3], wse[k], acc);
+                            st_stream1(oc + (size_t)r * p.W + h * 32, acc);
+                        }
+                }
+            });
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&empty_bar[s]);
+        }
+        return;
+    }
+
+    // edge tile (partial, or taps clamped at the right image border): generic loop
     PixelTaps tp[PPT];
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
         const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
         const int rx = t.x0 - bx0, ry = t.y0 - by0;
         const int ry1 = ry + (t.y1ok ? 1 : 0);
-        tp[k].off_n = (ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * BW + rx;
-        tp[k].off_s = (ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * BW + rx;
+        tp[k].off_n = (ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * Cfg::ROW_PITCH + rx;
+        tp[k].off_s = (ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * Cfg::ROW_PITCH + rx;
         tp[k].dx = t.x1ok ? 1 : 0;
         // a tap outside the image contributes nothing (ATen skips it): zero its weight,
         // its (clamped) address stays inside the staged box
@@ -243,7 +360,6 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
         tp[k].se = (t.x1ok && t.y1ok) ? t.se : 0.0f;
         if (!valid[k]) { tp[k].off_n = tp[k].off_s = 0; tp[k].dx = 0; }
     }
-    float* obase = out + (size_t)plane0 * plane + (size_t)(ty0 + warp * RPW) * p.W + tx0 + lane;
     for (int g = 0; g < ngroups; ++g) {
         const int s = g % STAGES;
         tma::mbar_wait(&full_bar[s], (g / STAGES) & 1);
@@ -252,23 +368,21 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
         for (int c = 0; c < CC; ++c) {
             const int ch = g * CC + c;
             if (ch < p.C) {
-                const float* sc = sb + c * (Cfg::ROWCHUNK * BW);
+                const float* sc = sb + c * BW;
                 float* oc = obase + (size_t)ch * plane;
-                float res[PPT];
-#pragma unroll
-                for (int k = 0; k < PPT; ++k) {
-                    const float a = sc[tp[k].off_n], bq = sc[tp[k].off_n + tp[k].dx];
-                    const float cq = sc[tp[k].off_s], d = sc[tp[k].off_s + tp[k].dx];
-                    float acc = __fmul_rn(a, tp[k].nw);
-                    acc = fmaf(bq, tp[k].ne, acc);
-                    acc = fmaf(cq, tp[k].sw, acc);
-                    res[k] = fmaf(d, tp[k].se, acc);
-                }
 #pragma unroll
                 for (int r = 0; r < RPW; ++r)
 #pragma unroll
-                    for (int h = 0; h < XH; ++h)
-                        if (valid[r * XH + h]) st_stream1(oc + (size_t)r * p.W + h * 32, res[r * XH + h]);
+                    for (int h = 0; h < XH; ++h) {
+                        const int k = r * XH + h;
+                        const float a = sc[tp[k].off_n], bq = sc[tp[k].off_n + tp[k].dx];
+                        const float cq = sc[tp[k].off_s], d = sc[tp[k].off_s + tp[k].dx];
+                        float acc = __fmul_rn(a, tp[k].nw);
+                        acc = fmaf(bq, tp[k].ne, acc);
+                        acc = fmaf(cq, tp[k].sw, acc);
+                        acc = fmaf(d, tp[k].se, acc);
+                        if (valid[k]) st_stream1(oc + (size_t)r * p.W + h * 32, acc);
+                    }
             }
         }
         __syncwarp();
@@ -295,15 +409,22 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
+int dsvc_warp_deferred_launch(const float* input, const float* flow, float* out,
+                              const float* lin_x, const float* lin_y, const WarpParams& p,
+                              const DeferredTiles* list, int tile_w, int tile_h, int tiles_x,
+                              int tiles_y, cudaStream_t st);  // warp_gather.cu
+
 template <class Cfg>
 static int launch_cfg(const float* input, const float* flow, float* out, const float* lin_x,
-                      const float* lin_y, const WarpParams& p, cudaStream_t st) {
+                      const float* lin_y, const WarpParams& p, void* workspace,
+                      size_t workspace_bytes, cudaStream_t st) {
     auto encode = get_encode_fn();
     if (!encode) return -1;
     CUtensorMap tm;
-    const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B * p.C};
-    const cuuint64_t gstride[2] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H * p.W * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::ROWCHUNK, (cuuint32_t)Cfg::CC};
+    // tensor viewed as (x, plane, y): the box lands in shared memory as [8 rows][CC][BW]
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)p.B * p.C, (cuuint64_t)p.H};
+    const cuuint64_t gstride[2] = {(cuuint64_t)p.H * p.W * 4, (cuuint64_t)p.W * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::CC, (cuuint32_t)Cfg::ROWCHUNK};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(input),
                               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -319,19 +440,44 @@ static int launch_cfg(const float* input, const float* flow, float* out, const f
         attr_set = true;
     }
     dim3 grid((p.W + Cfg::TW - 1) / Cfg::TW, (p.H + Cfg::TH - 1) / Cfg::TH, p.B);
+    const size_t ntiles = (size_t)grid.x * grid.y * grid.z;
+    DeferredTiles* list = nullptr;
+    if (workspace && workspace_bytes >= sizeof(DeferredTiles) + ntiles * sizeof(int) &&
+        aligned16(workspace)) {
+        list = static_cast<DeferredTiles*>(workspace);
+        cudaError_t e = cudaMemsetAsync(&list->count, 0, sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+    }
     warp_fwd_tma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tm, input, flow, out,
-                                                                          lin_x, lin_y, p);
-    return (int)cudaGetLastError();
+                                                                          lin_x, lin_y, p, list);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !list) return (int)e;
+    return dsvc_warp_deferred_launch(input, flow, out, lin_x, lin_y, p, list, Cfg::TW, Cfg::TH,
+                                     (int)grid.x, (int)grid.y, st);
 }
 
 // returns -1 when the shape is not eligible (caller uses the gather kernel)
 int dsvc_warp_fwd_tma_launch(const float* input, const float* flow, float* out,
                              const float* lin_x, const float* lin_y, const WarpParams& p,
-                             bool force, cudaStream_t st) {
+                             bool force, void* workspace, size_t workspace_bytes,
+                             cudaStream_t st) {
     // TMA needs 16-byte aligned rows and base; small / few-channel warps gain nothing
     if (p.W % 4 != 0 || !aligned16(input)) return -1;
     if (!force && (p.C < 8 || p.W < 64 || p.H < 32)) return -1;
     if ((long long)p.B * p.C > (1ll << 30)) return -1;
-    using Cfg = TmaCfg<64, 32, 80, 48, 2, 3>;
-    return launch_cfg<Cfg>(input, flow, out, lin_x, lin_y, p, st);
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("DSVC_TMA_CFG");  // tuning knob
+        cfg = e ? atoi(e) : 0;
+    }
+    switch (cfg) {
+        case 1: return launch_cfg<TmaCfg<64, 32, 96, 48, 2, 2>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 2: return launch_cfg<TmaCfg<64, 32, 80, 48, 4, 2>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 3: return launch_cfg<TmaCfg<64, 16, 80, 32, 2, 3>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 4: return launch_cfg<TmaCfg<64, 16, 80, 32, 4, 3>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 5: return launch_cfg<TmaCfg<32, 32, 48, 48, 2, 4>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 6: return launch_cfg<TmaCfg<64, 32, 80, 48, 2, 2>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 7: return launch_cfg<TmaCfg<64, 16, 80, 32, 2, 4>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        default: return launch_cfg<TmaCfg<64, 32, 80, 48, 2, 3>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+    }
 }

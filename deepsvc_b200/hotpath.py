@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .entropy import EntropyBottleneck, GaussianConditional, _common_rows
-from .warp import _base_grids, _scales
+from .warp import _base_grids, _scales, warp_workspace
 
 NUM_SLICES = 8
 
@@ -114,11 +114,12 @@ class PFrameHotPath:
         out = torch.empty_like(inp)
         lin_x, lin_y = _base_grids(inp.device, H, W)
         sx, sy, inv_sx, inv_sy = _scales(H, W)
-        self._keep += [out, lin_x, lin_y]
+        ws = warp_workspace(inp.device, B, H, W) if C >= 8 else None
+        self._keep += [out, lin_x, lin_y, ws]
         self._calls.append((self.lib.dsvc_warp_fwd_f32, (
             inp.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, lin_x.data_ptr(),
             lin_y.data_ptr(), sx, sy, inv_sx, inv_sy, self.flow_mode, _lib.LAYOUT_NCHW,
-            self.warp_algo), f"warp_c{C}_{H}x{W}"))
+            self.warp_algo, _lib.ptr(ws), 0 if ws is None else ws.numel()), f"warp_c{C}_{H}x{W}"))
         return out
 
     def run(self):

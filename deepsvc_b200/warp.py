@@ -49,6 +49,13 @@ def _base_grids(device, H, W):
     return g
 
 
+def warp_workspace(device, B, H, W):
+    """Scratch for the staged kernel's deferred-tile list: a fresh tensor from torch's
+    caching allocator (stream-ordered, so concurrent streams never share it)."""
+    n = _lib.load().dsvc_warp_workspace_bytes(B, H, W)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
 def _scales(H, W):
     sx = np.float32((W - 1.0) / 2.0)
     sy = np.float32((H - 1.0) / 2.0)
@@ -94,12 +101,14 @@ def warp_forward(inp, flow, flow_mode=None, algo=None):
     lin_x, lin_y = _base_grids(inp.device, H, W)
     sx, sy, inv_sx, inv_sy = _scales(H, W)
     lib = _lib.load()
+    ws = warp_workspace(inp.device, B, H, W) if (layout == _lib.LAYOUT_NCHW and C >= 8) else None
     with torch.cuda.device(inp.device):
         err = lib.dsvc_warp_fwd_f32(
             inp.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W,
             lin_x.data_ptr(), lin_y.data_ptr(), sx, sy, inv_sx, inv_sy,
             _flow_mode if flow_mode is None else flow_mode, layout,
-            _algo if algo is None else algo, _lib.stream_ptr(inp.device))
+            _algo if algo is None else algo, _lib.ptr(ws), 0 if ws is None else ws.numel(),
+            _lib.stream_ptr(inp.device))
     _lib.check(err, "dsvc_warp_fwd_f32")
     return out
 

@@ -63,12 +63,20 @@ int dsvc_device_arch(void);
  * lin_x[W], lin_y[H]: the reference's torch.linspace(-1,1,W|H) base grids
  * (modules.py:47-50), passed in so that the CPU-computed table is reproduced
  * bit for bit.  flow is always NCHW [B,2,H,W] (ch0 = dx, ch1 = dy, pixels).
- * input/out: [B,C,H,W] in `layout`. */
+ * input/out: [B,C,H,W] in `layout`.
+ *
+ * workspace (device, 16-byte aligned, nullable): scratch of at least
+ * dsvc_warp_workspace_bytes(B, H, W) bytes.  With it, tiles whose source bounding box
+ * cannot be staged are handed to a second, full-occupancy gather launch instead of
+ * being processed by one slow CTA; without it they are gathered in place.  Results are
+ * identical either way.  The scratch is only used during the call's own launches. */
 int dsvc_warp_fwd_f32(const float* input, const float* flow, float* out,
                       int B, int C, int H, int W,
                       const float* lin_x, const float* lin_y,
                       float sx, float sy, float inv_sx, float inv_sy,
-                      int flow_mode, int layout, int algo, void* stream);
+                      int flow_mode, int layout, int algo,
+                      void* workspace, size_t workspace_bytes, void* stream);
+size_t dsvc_warp_workspace_bytes(int B, int H, int W);
 
 /* Gradient of the above (autograd of modules.py:25-62 = ATen
  * grid_sampler_2d_backward + the division by sx/sy).
@@ -158,6 +166,36 @@ int dsvc_eb_bwd_f32(const float* grad_lik, const float* z, const float* noise,
  * video_model.py:39-42.  seg_offsets is a DEVICE int32 array [nseg+1]. */
 int dsvc_bits_finalize_f64(const double* partials, const int32_t* seg_offsets,
                            const double* scales, double* out, int nseg, void* stream);
+
+/* ------------------------------------------------------------------------------
+ * Host-side range coder ("next" rows f-1 / f-2 of SURVEY.md 8f).  HOST pointers.
+ * Replaces the native extension of the reference's dependency (compressai 1.2.1
+ * cpp_exts/rans/rans_interface.cpp + cpp_exts/ops/ops.cpp) as used at
+ * image_model.py:217-221,253-254,266-274,288,319-324.  Same wire format (rANS64,
+ * 32-bit words, 16-bit precision, 4-bit bypass), so streams interoperate.
+ * cdfs is a row-major int32 table [n_cdfs, cdf_stride]; cdf_sizes / offsets [n_cdfs]. */
+
+/* compressai._CXX.pmf_to_quantized_cdf: pmf[n] -> cdf_out[n+1], strictly increasing,
+ * cdf_out[n] = 1 << precision. */
+int dsvc_pmf_to_quantized_cdf_host(const float* pmf, int n, int precision, int32_t* cdf_out);
+
+/* compressai.ans.BufferedRansEncoder: push any number of (symbols, indexes) runs, then
+ * flush once (image_model.py:221,253-254). */
+void* dsvc_rans_encoder_create(void);
+void dsvc_rans_encoder_destroy(void* enc);
+int dsvc_rans_encoder_push(void* enc, const int32_t* symbols, const int32_t* indexes, int64_t n,
+                           const int32_t* cdfs, int n_cdfs, int cdf_stride,
+                           const int32_t* cdf_sizes, const int32_t* offsets);
+int64_t dsvc_rans_encoder_bound(void* enc);
+int dsvc_rans_encoder_flush(void* enc, uint8_t* out, int64_t out_cap, int64_t* out_len);
+
+/* compressai.ans.RansDecoder: set_stream once, decode_stream per slice
+ * (image_model.py:273-274,288). */
+void* dsvc_rans_decoder_create(const uint8_t* stream, int64_t len);
+void dsvc_rans_decoder_destroy(void* dec);
+int dsvc_rans_decoder_decode(void* dec, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                             int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                             const int32_t* offsets, int32_t* out_symbols);
 
 #ifdef __cplusplus
 }
