@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flow", default="smooth", choices=["smooth", "stress", "border"])
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tma"])
+    ap.add_argument("--serial", action="store_true",
+                    help="capture the frame's 25 launches in serial order instead of as a DAG")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 40)")
@@ -240,7 +242,7 @@ def run_ours(args):
     models = build_models(dev)
     gpu_in = synthetic.to_device(cpu_in, dev)
     hp = PFrameHotPath(gpu_in, models, warp_algo=algo)
-    hp.capture()
+    hp.capture(dag=not args.serial)
     bytes_alg = synthetic.pframe_algorithmic_bytes(B, Hh, Ww)
 
     def barrier():
@@ -337,7 +339,11 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "flow": args.flow, "warp_algo": args.algo,
                        "per_gpu": "each rank codes its own independent sequence (no data-path collective)",
                        "l2": "inputs larger than L2: 1.26 GB working set per frame vs 126 MB L2, no flush needed",
-                       "launch": "CUDA graph replay of the 25-launch frame", "bpp_check": bpp},
+                       "launch": ("CUDA graph replay of the frame's 25 hot-path launches, "
+                                  + ("serial order" if args.serial else
+                                     "captured as their data-dependency DAG (4 branches: feature warp | "
+                                     "3-ch warps | mv entropy | res entropy, joined by bits_finalize)")),
+                       "bpp_check": bpp},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": hp.n_launches * args.steps, "clocks": sampler.summary(),
         }

@@ -131,8 +131,46 @@ class PFrameHotPath:
                 if err:
                     _lib.check(err, name)
 
-    def capture(self):
-        """Capture ``run()`` into a CUDA graph (after a warm-up run on a side stream)."""
+    def _branch_of(self, name: str) -> str:
+        if name == "bits_finalize":
+            return "final"
+        if name.startswith("warp_"):
+            return "feature" if name.startswith(f"warp_c{self.inputs['feature'].shape[1]}_") and \
+                self.inputs["feature"].shape[1] != 3 else "frames"
+        return "mv" if name.endswith("_mv") else "res"
+
+    def run_dag(self, streams: dict):
+        """Enqueue the frame as its data-dependency DAG: the ops of one frame's hot path
+        do not consume each other's outputs (the reference's slice-to-slice order comes
+        from conv transforms outside the path), only the bit sums join the 18 entropy
+        launches.  Four branches fork from the current stream and join before
+        ``bits_finalize``: feature warp | the five 3-ch warps | mv entropy | res entropy."""
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        with torch.cuda.device(self.device):
+            for bname, st in streams.items():
+                st.wait_event(fork)
+                for fn, args, name in self._calls:
+                    if self._branch_of(name) == bname:
+                        err = fn(*args, st.cuda_stream)
+                        if err:
+                            _lib.check(err, name)
+                ev = torch.cuda.Event()
+                ev.record(st)
+                joins.append(ev)
+            for ev in joins:
+                main.wait_event(ev)
+            for fn, args, name in self._calls:
+                if self._branch_of(name) == "final":
+                    err = fn(*args, main.cuda_stream)
+                    if err:
+                        _lib.check(err, name)
+
+    def capture(self, dag: bool = True):
+        """Capture the frame into a CUDA graph (after a warm-up run on a side stream).
+        dag=True captures the dependency DAG (``run_dag``), dag=False the serial order."""
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -140,9 +178,15 @@ class PFrameHotPath:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
+        if dag:
+            self._streams = {b: torch.cuda.Stream(self.device) for b in ("feature", "frames", "mv", "res")}
         with torch.cuda.graph(g):
-            self.run()
+            if dag:
+                self.run_dag(self._streams)
+            else:
+                self.run()
         self._graph = g
+        self.dag = dag
         return g
 
     def replay(self):
