@@ -5,7 +5,7 @@ Host-side mirror of the reference's operator interface for this path
 / ``ste_round`` / ``LowerBound``) on top of the C ABI in ``include/deepsvc_b200.h``.
 Importing the package does not require a GPU; calling an op does (no CPU fallback).
 """
-from . import _lib
+from . import _lib, ans
 from .warp import torch_warp, warp_forward, warp_backward, set_flow_arithmetic, set_warp_algorithm
 from .entropy import (EntropyBottleneck, EntropyModel, GaussianConditional, LowerBound, ste_round,
                       bits_finalize, bpp_scale)

@@ -288,6 +288,67 @@ class EntropyModel(nn.Module):
     def _dequantize(cls, inputs, means=None):
         return cls.dequantize(inputs, means)
 
+    # ---- range coding (compressai EntropyModel.compress / .decompress; call sites
+    # image_model.py:206-207 through EntropyBottleneck).  Symbols are computed by the fused
+    # kernel and leave the device in ONE int32 copy per batch item; the coding loop is
+    # csrc/coder.cpp.
+    def _check_tables(self):
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if len(self._quantized_cdf.size()) != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+
+    def _cdf_tables(self):
+        from .ans import CdfTables
+        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version,
+               self._offset.data_ptr(), self._cdf_length.data_ptr())
+        if getattr(self, "_tables_cache", None) is None or self._tables_cache[0] != key:
+            self._tables_cache = (key, CdfTables(self._quantized_cdf, self._cdf_length, self._offset))
+        return self._tables_cache[1]
+
+    def compress(self, inputs, indexes, means=None):
+        from .ans import RansEncoder
+        symbols = self.quantize(inputs, "symbols", means)
+        if len(inputs.size()) < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_tables()
+        tables = self._cdf_tables()
+        sym = symbols.cpu()
+        idx = indexes.int().cpu()
+        return [RansEncoder().encode_with_indexes(sym[i], idx[i], tables) for i in range(sym.size(0))]
+
+    def decompress(self, strings, indexes, dtype: torch.dtype = torch.float, means=None):
+        from .ans import RansDecoder
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if len(indexes.size()) < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_tables()
+        if means is not None:
+            if means.size()[:2] != indexes.size()[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size():
+                for i in range(2, len(indexes.size())):
+                    if means.size(i) != 1:
+                        raise ValueError("Invalid means parameters")
+        tables = self._cdf_tables()
+        idx = indexes.int().cpu()
+        out = torch.empty(indexes.size(), dtype=torch.int32)
+        for i, s in enumerate(strings):
+            dec = RansDecoder()
+            dec.set_stream(s)
+            out[i] = torch.from_numpy(dec.decode_stream_array(idx[i], tables)).reshape(out[i].size())
+        dev = means.device if means is not None else self._quantized_cdf.device
+        return self.dequantize(out.to(dev), means, dtype)
+
 
 # --------------------------------------------------------------------------- Gaussian
 class GaussianConditional(EntropyModel):
@@ -590,6 +651,38 @@ class EntropyBottleneck(EntropyModel):
         self._offset = offset.to(dev)
         self._cdf_length = length.to(dev)
         return True
+
+    @staticmethod
+    def _build_indexes(size):
+        dims = len(size)
+        N = size[0]
+        C = size[1]
+        view_dims = np.ones((dims,), dtype=np.int64)
+        view_dims[1] = -1
+        indexes = torch.arange(C).view(*view_dims)
+        indexes = indexes.int()
+        return indexes.repeat(N, 1, *size[2:])
+
+    @staticmethod
+    def _extend_ndims(tensor, n):
+        return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
+
+    def compress(self, x):
+        """``image_model.py:206``: per-channel table index, medians as means."""
+        indexes = self._build_indexes(x.size())
+        medians = self._get_medians().detach()
+        spatial_dims = len(x.size()) - 2
+        medians = self._extend_ndims(medians, spatial_dims)
+        medians = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+        return super().compress(x, indexes, medians)
+
+    def decompress(self, strings, size):
+        """``image_model.py:207,260``."""
+        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+        indexes = self._build_indexes(output_size)
+        medians = self._extend_ndims(self._get_medians().detach(), len(size))
+        medians = medians.expand(len(strings), *([-1] * (len(size) + 1)))
+        return super().decompress(strings, indexes, medians.dtype, medians)
 
     def _run(self, x, training, want_bits, noise=None):
         if training is None:

@@ -3,6 +3,7 @@
 The reference has no plugin registry; its hot path is reached through three kinds of
 names:
 
+0. (also rebinds ``image_model.BufferedRansEncoder`` / ``RansDecoder`` to the C++ coder)
 1. the module-level function ``modules.torch_warp``, imported *by name* into
    ``video_model`` (``video_model.py:3``) -> both bindings are replaced;
 2. the ``gaussian_conditional`` / ``entropy_bottleneck`` attributes of every
@@ -33,6 +34,22 @@ def patch_reference(modules_mod=None, video_model_mod=None, image_model_mod=None
     if image_model_mod is not None and hasattr(image_model_mod, "ste_round"):
         _saved.setdefault((image_model_mod.__name__, "ste_round"), image_model_mod.ste_round)
         image_model_mod.ste_round = _entropy.ste_round
+    # class names imported by name (image_model.py:4, video_model.py:5): models built after
+    # patching construct the drop-ins directly, and the isinstance() checks of
+    # aux_loss() (image_model.py:326-328, video_model.py:169-177) see the swapped modules
+    for mod in (image_model_mod, video_model_mod):
+        if mod is None:
+            continue
+        for attr in ("EntropyBottleneck", "GaussianConditional"):
+            if hasattr(mod, attr):
+                _saved.setdefault((mod.__name__, attr), getattr(mod, attr))
+                setattr(mod, attr, getattr(_entropy, attr))
+    if image_model_mod is not None:
+        from . import ans as _ans
+        for attr in ("BufferedRansEncoder", "RansDecoder"):   # image_model.py:8
+            if hasattr(image_model_mod, attr):
+                _saved.setdefault((image_model_mod.__name__, attr), getattr(image_model_mod, attr))
+                setattr(image_model_mod, attr, getattr(_ans, attr))
     return [k for k in _saved]
 
 

@@ -116,3 +116,60 @@ def test_dropin_on_reference_shaped_codec(oracle):
     (torch.log(l_got).sum() + torch.log(zl_got).sum()).backward()
     assert m.g_a.weight.grad is not None and torch.isfinite(m.g_a.weight.grad).all()
     assert m.entropy_bottleneck._matrix0.grad is not None
+
+
+def test_codec_path_bitstreams_match_oracle(oracle):
+    """The real-coding call pattern of image_model.py:201-302 (EB compress/decompress,
+    per-slice build_indexes + quantize("symbols"), one buffered rANS stream, slice-by-slice
+    decode + dequantize): GPU symbols/indexes + C++ coder vs the oracle's CPU path +
+    pure-Python coder.  Streams are byte-identical and decode to the same y_hat."""
+    import deepsvc_b200 as dsvc
+    from deepsvc_b200 import ans, synthetic
+    from compressai import ans as oans
+    dev = torch.device("cuda:0")
+    C, h, w = 16, 10, 14
+    eb_o, gc_o = oracle.make_entropy_models(C, seed=11)
+    eb_o.update(force=True)
+    eb = dsvc.EntropyBottleneck(C)
+    eb.load_state_dict({k: v for k, v in eb_o.state_dict().items()
+                        if k not in ("_offset", "_quantized_cdf", "_cdf_length")}, strict=False)
+    eb = eb.to(dev).eval()
+    eb.update(force=True)
+    gc = dsvc.GaussianConditional(None).to(dev).eval()
+    gc.update_scale_table(oracle.get_scale_table())
+    assert torch.equal(gc.quantized_cdf.cpu(), gc_o.quantized_cdf)
+    assert torch.equal(eb.quantized_cdf.cpu(), eb_o.quantized_cdf)
+
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(1, C, 3, 4, generator=g) * 4
+    z[0, 0, 0, 0] = 200.0   # outside the table -> bypass coding
+    z_str_o = eb_o.compress(z)
+    z_str = eb.compress(z.to(dev))
+    assert z_str == z_str_o
+    z_hat = eb.decompress(z_str, z.shape[-2:])
+    assert torch.equal(z_hat.cpu(), eb_o.decompress(z_str_o, z.shape[-2:]))
+
+    y, s, m = synthetic.make_latents(1, C, h, w, g)
+    y[0, 1, 2, 3] = m[0, 1, 2, 3] + 3000.0   # bypass
+    yd, sd, md = y.to(dev), s.to(dev), m.to(dev)
+    enc_o = oans.BufferedRansEncoder()
+    enc = ans.BufferedRansEncoder()
+    tables = gc._cdf_tables()
+    for ys, ss, ms, yo, so, mo in zip(yd.chunk(4, 1), sd.chunk(4, 1), md.chunk(4, 1),
+                                      y.chunk(4, 1), s.chunk(4, 1), m.chunk(4, 1)):
+        idx_o = gc_o.build_indexes(so)
+        sym_o = gc_o.quantize(yo, "symbols", mo)
+        enc_o.encode_with_indexes(sym_o.reshape(-1).tolist(), idx_o.reshape(-1).tolist(),
+                                  gc_o.quantized_cdf.tolist(), gc_o.cdf_length.tolist(), gc_o.offset.tolist())
+        sym, idx, y_hat = gc.quantize_and_index(ys, ss, ms)
+        assert torch.equal(sym.cpu(), sym_o) and torch.equal(idx.cpu(), idx_o)
+        enc.encode_with_indexes(sym, idx, tables)   # device tensors -> one int32 copy each
+    stream_o, stream = enc_o.flush(), enc.flush()
+    assert stream == stream_o
+    dec = ans.RansDecoder()
+    dec.set_stream(stream)
+    for ss, ms, yo, mo in zip(sd.chunk(4, 1), md.chunk(4, 1), y.chunk(4, 1), m.chunk(4, 1)):
+        idx = gc.build_indexes(ss)
+        rv = torch.from_numpy(dec.decode_stream_array(idx, tables)).reshape(ss.shape).to(dev)
+        y_hat = gc.dequantize(rv, ms)
+        assert torch.equal(y_hat.cpu(), oracle.ste_round(yo - mo) + mo)
