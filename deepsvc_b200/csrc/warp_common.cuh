@@ -55,7 +55,7 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
 }
 
 // One thread: output pixel (x, y) of batch item b, channels [c0, cend) -- the direct
-// read-only-path gather (used by the gather kernel and by the deferred-tile kernel).
+// read-only-path gather (used by the gather kernel and by the staged kernel's work-list epilogue).
 template <int UNROLL>
 __device__ __forceinline__ void gather_pixel(const float* __restrict__ in,
                                              const float* __restrict__ flow,
@@ -108,11 +108,14 @@ __device__ __forceinline__ void gather_pixel(const float* __restrict__ in,
     }
 }
 
-// Work list of tiles the staged kernel could not stage (bounding box too large).
-struct DeferredTiles {
-    int count;
-    int pad[3];
-    int tiles[1];  // linear tile ids: (b * tiles_y + ty) * tiles_x + tx
+// Work list of tiles the staged kernel could not stage (bounding box too large).  Lives
+// in the caller's workspace, which is all-zero before and after every launch.
+struct WarpWork {
+    int count;     // tile slots reserved by appenders
+    int next;      // work items claimed so far (items, not tiles)
+    int exited;    // CTAs that have signed off; the last one re-zeroes the list
+    int pad;
+    int items[1];  // tile id + 1 per slot (0 = not yet published)
 };
 
 }  // namespace dsvc

@@ -27,36 +27,6 @@ warp_fwd_nchw_gather(const float* __restrict__ in, const float* __restrict__ flo
     gather_pixel<UNROLL>(in, flow, out, lin_x, lin_y, p, b, x, y, c0, min(p.C, c0 + cpc));
 }
 
-// Tiles deferred by the staged kernel (warp_tma.cu): a persistent grid walks the work
-// list; one work item = a 32 x 8 pixel block x 16 channels of a deferred tile, i.e. the
-// same CTA shape (and occupancy) as the gather kernel above.
-__global__ void __launch_bounds__(256)
-warp_fwd_deferred_tiles(const float* __restrict__ in, const float* __restrict__ flow,
-                        float* __restrict__ out, const float* __restrict__ lin_x,
-                        const float* __restrict__ lin_y, WarpParams p,
-                        const DeferredTiles* __restrict__ list, int tile_w, int tile_h,
-                        int tiles_x, int tiles_y) {
-    const int count = list->count;
-    if (count == 0) return;
-    constexpr int CPC = 16;
-    const int nchunk = (p.C + CPC - 1) / CPC;
-    const int bx = tile_w / 32, by = tile_h / 8;
-    const int per_tile = bx * by * nchunk;
-    const long long total = (long long)count * per_tile;
-    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const int t = list->tiles[w / per_tile];
-        int r = (int)(w % per_tile);
-        const int chunk = r % nchunk; r /= nchunk;
-        const int sx = r % bx, sy = r / bx;
-        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
-        const int x = tx * tile_w + sx * 32 + threadIdx.x;
-        const int y = ty * tile_h + sy * 8 + threadIdx.y;
-        if (x < p.W && y < p.H)
-            gather_pixel<4>(in, flow, out, lin_x, lin_y, p, b, x, y, chunk * CPC,
-                            min(p.C, chunk * CPC + CPC));
-    }
-}
-
 // ------------------------------------------------------------------ NHWC forward
 // channels_last: every tap is C contiguous floats -> pure 128-bit loads.  G lanes
 // cooperate on one pixel (G*16 bytes per tap per instruction), C % 4 == 0.
@@ -188,17 +158,6 @@ warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
 
 using namespace dsvc;
 
-int dsvc_warp_deferred_launch(const float* input, const float* flow, float* out,
-                              const float* lin_x, const float* lin_y, const WarpParams& p,
-                              const DeferredTiles* list, int tile_w, int tile_h, int tiles_x,
-                              int tiles_y, cudaStream_t st) {
-    dim3 block(32, 8);
-    warp_fwd_deferred_tiles<<<DSVC_NUM_SMS * 8, block, 0, st>>>(input, flow, out, lin_x, lin_y, p,
-                                                               list, tile_w, tile_h, tiles_x,
-                                                               tiles_y);
-    return (int)cudaGetLastError();
-}
-
 int dsvc_warp_fwd_tma_launch(const float* input, const float* flow, float* out,
                              const float* lin_x, const float* lin_y, const WarpParams& p,
                              bool force, void* workspace, size_t workspace_bytes,
@@ -247,8 +206,13 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
     const int nchunk = (C + cpc - 1) / cpc;
     DSVC_CHECK_ARG((int64_t)B * nchunk <= 65535);
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B * nchunk);
+    // all taps of up to 4 channels in flight per thread (C = 3 frames: 12 loads at once)
     if (cpc >= 4)
         warp_fwd_nchw_gather<4><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
+    else if (cpc == 3)
+        warp_fwd_nchw_gather<3><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
+    else if (cpc == 2)
+        warp_fwd_nchw_gather<2><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
     else
         warp_fwd_nchw_gather<1><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
     DSVC_RETURN_LAST();
@@ -256,9 +220,9 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
 
 extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    // deferred-tile list: header + one int per tile of the smallest staged tile (32 x 16)
+    // work list: header + one int per tile of the smallest staged tile (32 x 16)
     const size_t ntiles = (size_t)B * ((W + 31) / 32) * ((H + 15) / 16);
-    return sizeof(DeferredTiles) + ntiles * sizeof(int) + 16;
+    return sizeof(WarpWork) + ntiles * sizeof(int) + 16;
 }
 
 extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,

@@ -17,8 +17,20 @@
 //      instead of two L1 wavefronts per unaligned global gather) and store coalesced
 //      128-byte rows.
 // Coordinates and weights are computed once per pixel and reused for all C channels.
-// A tile whose bounding box does not fit the staging box (wild flow) falls back to the
-// read-only-path gather inside the same kernel, so results never depend on the path.
+//
+// Work decomposition: grid = (tiles_x, tiles_y, B * csplit).  A CTA stages its tile for
+// one of `csplit` channel ranges; the host picks csplit so that the number of CTAs is
+// close to a whole number of waves of 2 CTAs x 148 SMs (at 1080p: 1020 tiles = 3.45
+// waves -> 2040 half-channel units = 6.9 waves).
+//
+// A tile whose bounding box does not fit the staging box (wild flow) is cut into
+// (32 x 8 pixel) x (8 channel) work items on a device work list (WarpWork).  Every CTA,
+// after finishing its own tile, claims items from that list until it is empty, so the
+// rare unstageable tiles are gathered by the whole grid inside the same launch (same
+// arithmetic, bit-identical results) instead of by one slow CTA or a second launch.
+// The last CTA to finish re-zeroes the list: the workspace is zero before and after
+// every launch, no memset is needed.
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 #include <utility>
@@ -77,6 +89,11 @@ __device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* tmap,
         : "memory");
 }
 
+// named barrier over the consumer warps only (the producer warp has returned)
+__device__ __forceinline__ void bar_sync_consumers(int nthreads) {
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
 template <class F, int... Is>
 __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
     (f(std::integral_constant<int, Is>{}), ...);
@@ -125,7 +142,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 2)
 warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in,
                     const float* __restrict__ flow, float* __restrict__ out,
                     const float* __restrict__ lin_x, const float* __restrict__ lin_y,
-                    WarpParams p, DeferredTiles* __restrict__ deferred) {
+                    WarpParams p, WarpWork* __restrict__ work, int csplit, int cper) {
     constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, CC = Cfg::CC, STAGES = Cfg::STAGES;
     constexpr int RPW = Cfg::ROWS_PER_WARP, XH = Cfg::XH, PPT = Cfg::PPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -133,10 +150,13 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ int s_red[Cfg::CONSUMER_WARPS][4];
+    __shared__ int s_item;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_producer = warp == Cfg::CONSUMER_WARPS;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH, b = blockIdx.z;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    const int b = blockIdx.z / csplit, cpart = blockIdx.z - b * csplit;
+    const int c_begin = cpart * cper, c_end = min(p.C, c_begin + cper);  // this CTA's channels
     const size_t plane = (size_t)p.H * p.W;
 
     if (threadIdx.x == 0) {
@@ -200,73 +220,15 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
     const int bx0 = mnx & ~3, by0 = mny;
     const int bw = min(mxx + 1, p.W - 1) - bx0 + 1;
     const int bh = min(mxy + 1, p.H - 1) - mny + 1;
-    const bool staged = bw <= BW && bh <= Cfg::BHMAX;  // CTA-uniform
+    const bool staged = bw <= BW && bh <= Cfg::BHMAX && c_begin < c_end;  // CTA-uniform
     const int nchunks = (bh + Cfg::ROWCHUNK - 1) / Cfg::ROWCHUNK;
-    const int ngroups = (p.C + CC - 1) / CC;
+    const int ngroups = (c_end - c_begin + CC - 1) / CC;
     const int plane0 = b * p.C;
 
-    if (!staged) {
-        // ---- fallback: direct gather of this tile (identical arithmetic).  Channel-outer
-        // loop so that all PPT pixels' taps (4*PPT independent loads) are in flight at once:
-        // a fallback CTA must not take much longer than a staged one, or it becomes the
-        // kernel's tail.
-        if (deferred != nullptr) {
-            // hand the tile to the deferred-tile kernel (full-occupancy gather) instead of
-            // letting one slow CTA become the tail of this launch
-            if (threadIdx.x == 0) {
-                const int slot = atomicAdd(&deferred->count, 1);
-                deferred->tiles[slot] = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-            }
-            return;
-        }
-        if (is_producer) return;
-        float w4[PPT][4];
-        int o_nw[PPT], ddx[PPT], ddy[PPT];
-#pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-            const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
-            w4[k][0] = t.nw;
-            w4[k][1] = t.x1ok ? t.ne : 0.0f;
-            w4[k][2] = t.y1ok ? t.sw : 0.0f;
-            w4[k][3] = (t.x1ok && t.y1ok) ? t.se : 0.0f;
-            o_nw[k] = valid[k] ? t.y0 * p.W + t.x0 : 0;
-            ddx[k] = (valid[k] && t.x1ok) ? 1 : 0;
-            ddy[k] = (valid[k] && t.y1ok) ? p.W : 0;
-        }
-        const float* ip = in + (size_t)plane0 * plane;
-        float* op = out + (size_t)plane0 * plane + (size_t)(ty0 + warp * RPW) * p.W + tx0 + lane;
-        constexpr int KB = PPT < 4 ? PPT : 4;  // pixels per load batch (register budget)
-        for (int c = 0; c < p.C; ++c) {
-#pragma unroll
-            for (int k0 = 0; k0 < PPT; k0 += KB) {
-                float v[KB][4];
-#pragma unroll
-                for (int j = 0; j < KB; ++j) {
-                    const float* q = ip + o_nw[k0 + j];
-                    v[j][0] = __ldg(q);
-                    v[j][1] = __ldg(q + ddx[k0 + j]);
-                    v[j][2] = __ldg(q + ddy[k0 + j]);
-                    v[j][3] = __ldg(q + ddy[k0 + j] + ddx[k0 + j]);
-                }
-#pragma unroll
-                for (int j = 0; j < KB; ++j) {
-                    const int k = k0 + j;
-                    float acc = __fmul_rn(v[j][0], w4[k][0]);
-                    acc = fmaf(v[j][1], w4[k][1], acc);
-                    acc = fmaf(v[j][2], w4[k][2], acc);
-                    acc = fmaf(v[j][3], w4[k][3], acc);
-                    if (valid[k]) st_stream1(op + (size_t)(k / XH) * p.W + (k % XH) * 32, acc);
-                }
-            }
-            ip += plane;
-            op += plane;
-        }
-        return;
-    }
-
     if (is_producer) {
-        // ---- phase 2 (producer warp, one elected lane): TMA ring over channel groups
-        if (lane == 0) {
+        // ---- phase 2 (producer warp, one elected lane): TMA ring over channel groups.
+        // The CTA outlives the loads: the consumers wait on every full barrier.
+        if (staged && lane == 0) {
             const uint32_t tx_bytes = (uint32_t)nchunks * Cfg::CHUNK_FLOATS * sizeof(float);
             for (int g = 0; g < ngroups; ++g) {
                 const int s = g % STAGES;
@@ -274,119 +236,180 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __res
                 tma::mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
                 float* dst = stage_buf + (size_t)s * Cfg::STAGE_FLOATS;
                 for (int k = 0; k < nchunks; ++k)
-                    tma::load_3d(dst + (size_t)k * Cfg::CHUNK_FLOATS, &tmap, bx0, plane0 + g * CC,
-                                 by0 + k * Cfg::ROWCHUNK, &full_bar[s]);
+                    tma::load_3d(dst + (size_t)k * Cfg::CHUNK_FLOATS, &tmap, bx0,
+                                 plane0 + c_begin + g * CC, by0 + k * Cfg::ROWCHUNK, &full_bar[s]);
             }
         }
         return;
     }
 
-    // ---- phase 3 (consumers): gather from the staged box, store coalesced rows.
-    // Shared-memory element (row ry, channel c, column rx) of a stage lives at
-    //   (ry >> 3) * CHUNK_FLOATS + (ry & 7) * ROW_PITCH + c * BW + rx.
-    const bool fast = (tx0 + TW <= p.W) && (ty0 + TH <= p.H) && (mxx + 1 < p.W);  // CTA-uniform
-    float* obase = out + (size_t)plane0 * plane + (size_t)(ty0 + warp * RPW) * p.W + tx0 + lane;
-    if (fast) {
-        // interior tile, every east tap inside the image: byte addresses, immediate offsets
-        float wnw[PPT], wne[PPT], wsw[PPT], wse[PPT];
-        uint32_t a_n[PPT], a_s[PPT];
-#pragma unroll
-        for (int k = 0; k < PPT; ++k) {
-            const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
-            const int rx = t.x0 - bx0, ry = t.y0 - by0;
-            const int ry1 = ry + (t.y1ok ? 1 : 0);
-            a_n[k] = 4u * (uint32_t)((ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * Cfg::ROW_PITCH + rx);
-            a_s[k] = 4u * (uint32_t)((ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * Cfg::ROW_PITCH + rx);
-            wnw[k] = t.nw;
-            wne[k] = t.ne;
-            wsw[k] = t.y1ok ? t.sw : 0.0f;
-            wse[k] = t.y1ok ? t.se : 0.0f;
+    if (!staged) {
+        // unstageable tile: publish it on the work list (once per tile); every CTA of the
+        // launch, this one included, helps to gather it in the epilogue below
+        if (cpart == 0 && threadIdx.x == 0 && bw > 0 && bh > 0) {
+            const int slot = atomicAdd(&work->count, 1);
+            const int tile = (b * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            *reinterpret_cast<volatile int*>(&work->items[slot]) = tile + 1;  // non-zero = ready
+            __threadfence();
         }
-        const uint32_t sbase0 = tma::smem_u32(stage_buf);
-        for (int g = 0; g < ngroups; ++g) {
-            const int s = g % STAGES;
-            tma::mbar_wait(&full_bar[s], (g / STAGES) & 1);
-            const uint32_t sbase = sbase0 + (uint32_t)s * (Cfg::STAGE_FLOATS * 4);
-            uint32_t tn[PPT], ts[PPT];
+    } else {
+        // ---- phase 3 (consumers): gather from the staged box, store coalesced rows.
+        // Shared-memory element (row ry, channel c, column rx) of a stage lives at
+        //   (ry >> 3) * CHUNK_FLOATS + (ry & 7) * ROW_PITCH + c * BW + rx.
+        const bool fast = (tx0 + TW <= p.W) && (ty0 + TH <= p.H) && (mxx + 1 < p.W);  // CTA-uniform
+        float* obase = out + (size_t)(plane0 + c_begin) * plane + (size_t)(ty0 + warp * RPW) * p.W + tx0 + lane;
+        if (fast) {
+            // interior tile, every east tap inside the image: byte addresses, immediate offsets
+            float wnw[PPT], wne[PPT], wsw[PPT], wse[PPT];
+            uint32_t a_n[PPT], a_s[PPT];
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) { tn[k] = a_n[k] + sbase; ts[k] = a_s[k] + sbase; }
-            tma::static_for<CC>([&](auto cc) {
-                constexpr int c = decltype(cc)::value;
-                const int ch = g * CC + c;
-                if (ch < p.C) {
-                    float v[PPT][4];
+            for (int k = 0; k < PPT; ++k) {
+                const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
+                const int rx = t.x0 - bx0, ry = t.y0 - by0;
+                const int ry1 = ry + (t.y1ok ? 1 : 0);
+                a_n[k] = 4u * (uint32_t)((ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * Cfg::ROW_PITCH + rx);
+                a_s[k] = 4u * (uint32_t)((ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * Cfg::ROW_PITCH + rx);
+                wnw[k] = t.nw;
+                wne[k] = t.ne;
+                wsw[k] = t.y1ok ? t.sw : 0.0f;
+                wse[k] = t.y1ok ? t.se : 0.0f;
+            }
+            const uint32_t sbase0 = tma::smem_u32(stage_buf);
+            for (int g = 0; g < ngroups; ++g) {
+                const int s = g % STAGES;
+                tma::mbar_wait(&full_bar[s], (g / STAGES) & 1);
+                const uint32_t sbase = sbase0 + (uint32_t)s * (Cfg::STAGE_FLOATS * 4);
+                uint32_t tn[PPT], ts[PPT];
 #pragma unroll
-                    for (int k = 0; k < PPT; ++k) {
-                        v[k][0] = tma::lds_imm<c * BW * 4>(tn[k]);
-                        v[k][1] = tma::lds_imm<c * BW * 4 + 4>(tn[k]);
-                        v[k][2] = tma::lds_imm<c * BW * 4>(ts[k]);
-                        v[k][3] = tma::lds_imm<c * BW * 4 + 4>(ts[k]);
-                    }
-                    float* oc = obase + (size_t)ch * plane;
+                for (int k = 0; k < PPT; ++k) { tn[k] = a_n[k] + sbase; ts[k] = a_s[k] + sbase; }
+                tma::static_for<CC>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    const int ch = g * CC + c;  // relative to c_begin
+                    if (c_begin + ch < c_end) {
+                        float v[PPT][4];
 #pragma unroll
-                    for (int r = 0; r < RPW; ++r)
-#pragma unroll
-                        for (int h = 0; h < XH; ++h) {
-                            const int k = r * XH + h;
-                            float acc = __fmul_rn(v[k][0], wnw[k]);
-                            acc = fmaf(v[k][1], wne[k], acc);
-                            acc = fmaf(v[k][2], wsw[k], acc);
-                            acc = fmaf(v[k][3], wse[k], acc);
-                            st_stream1(oc + (size_t)r * p.W + h * 32, acc);
+                        for (int k = 0; k < PPT; ++k) {
+                            v[k][0] = tma::lds_imm<c * BW * 4>(tn[k]);
+                            v[k][1] = tma::lds_imm<c * BW * 4 + 4>(tn[k]);
+                            v[k][2] = tma::lds_imm<c * BW * 4>(ts[k]);
+                            v[k][3] = tma::lds_imm<c * BW * 4 + 4>(ts[k]);
                         }
-                }
-            });
-            __syncwarp();
-            if (lane == 0) tma::mbar_arrive(&empty_bar[s]);
-        }
-        return;
-    }
-
-    // edge tile (partial, or taps clamped at the right image border): generic loop
-    PixelTaps tp[PPT];
+                        float* oc = obase + (size_t)ch * plane;
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-        const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
-        const int rx = t.x0 - bx0, ry = t.y0 - by0;
-        const int ry1 = ry + (t.y1ok ? 1 : 0);
-        tp[k].off_n = (ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * Cfg::ROW_PITCH + rx;
-        tp[k].off_s = (ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * Cfg::ROW_PITCH + rx;
-        tp[k].dx = t.x1ok ? 1 : 0;
-        // a tap outside the image contributes nothing (ATen skips it): zero its weight,
-        // its (clamped) address stays inside the staged box
-        tp[k].nw = t.nw;
-        tp[k].ne = t.x1ok ? t.ne : 0.0f;
-        tp[k].sw = t.y1ok ? t.sw : 0.0f;
-        tp[k].se = (t.x1ok && t.y1ok) ? t.se : 0.0f;
-        if (!valid[k]) { tp[k].off_n = tp[k].off_s = 0; tp[k].dx = 0; }
-    }
-    for (int g = 0; g < ngroups; ++g) {
-        const int s = g % STAGES;
-        tma::mbar_wait(&full_bar[s], (g / STAGES) & 1);
-        const float* sb = stage_buf + (size_t)s * Cfg::STAGE_FLOATS;
+                        for (int r = 0; r < RPW; ++r)
 #pragma unroll
-        for (int c = 0; c < CC; ++c) {
-            const int ch = g * CC + c;
-            if (ch < p.C) {
-                const float* sc = sb + c * BW;
-                float* oc = obase + (size_t)ch * plane;
-#pragma unroll
-                for (int r = 0; r < RPW; ++r)
-#pragma unroll
-                    for (int h = 0; h < XH; ++h) {
-                        const int k = r * XH + h;
-                        const float a = sc[tp[k].off_n], bq = sc[tp[k].off_n + tp[k].dx];
-                        const float cq = sc[tp[k].off_s], d = sc[tp[k].off_s + tp[k].dx];
-                        float acc = __fmul_rn(a, tp[k].nw);
-                        acc = fmaf(bq, tp[k].ne, acc);
-                        acc = fmaf(cq, tp[k].sw, acc);
-                        acc = fmaf(d, tp[k].se, acc);
-                        if (valid[k]) st_stream1(oc + (size_t)r * p.W + h * 32, acc);
+                            for (int h = 0; h < XH; ++h) {
+                                const int k = r * XH + h;
+                                float acc = __fmul_rn(v[k][0], wnw[k]);
+                                acc = fmaf(v[k][1], wne[k], acc);
+                                acc = fmaf(v[k][2], wsw[k], acc);
+                                acc = fmaf(v[k][3], wse[k], acc);
+                                st_stream1(oc + (size_t)r * p.W + h * 32, acc);
+                            }
                     }
+                });
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&empty_bar[s]);
+            }
+        } else {
+            // edge tile (partial, or taps clamped at the right image border): generic loop
+            PixelTaps tp[PPT];
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const Taps t = make_taps(ixs[k], iys[k], p.W, p.H);
+                const int rx = t.x0 - bx0, ry = t.y0 - by0;
+                const int ry1 = ry + (t.y1ok ? 1 : 0);
+                tp[k].off_n = (ry >> 3) * Cfg::CHUNK_FLOATS + (ry & 7) * Cfg::ROW_PITCH + rx;
+                tp[k].off_s = (ry1 >> 3) * Cfg::CHUNK_FLOATS + (ry1 & 7) * Cfg::ROW_PITCH + rx;
+                tp[k].dx = t.x1ok ? 1 : 0;
+                // a tap outside the image contributes nothing (ATen skips it): zero its weight,
+                // its (clamped) address stays inside the staged box
+                tp[k].nw = t.nw;
+                tp[k].ne = t.x1ok ? t.ne : 0.0f;
+                tp[k].sw = t.y1ok ? t.sw : 0.0f;
+                tp[k].se = (t.x1ok && t.y1ok) ? t.se : 0.0f;
+                if (!valid[k]) { tp[k].off_n = tp[k].off_s = 0; tp[k].dx = 0; }
+            }
+            for (int g = 0; g < ngroups; ++g) {
+                const int s = g % STAGES;
+                tma::mbar_wait(&full_bar[s], (g / STAGES) & 1);
+                const float* sb = stage_buf + (size_t)s * Cfg::STAGE_FLOATS;
+#pragma unroll
+                for (int c = 0; c < CC; ++c) {
+                    const int ch = g * CC + c;
+                    if (c_begin + ch < c_end) {
+                        const float* sc = sb + c * BW;
+                        float* oc = obase + (size_t)ch * plane;
+#pragma unroll
+                        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+                            for (int h = 0; h < XH; ++h) {
+                                const int k = r * XH + h;
+                                const float a = sc[tp[k].off_n], bq = sc[tp[k].off_n + tp[k].dx];
+                                const float cq = sc[tp[k].off_s], d = sc[tp[k].off_s + tp[k].dx];
+                                float acc = __fmul_rn(a, tp[k].nw);
+                                acc = fmaf(bq, tp[k].ne, acc);
+                                acc = fmaf(cq, tp[k].sw, acc);
+                                acc = fmaf(d, tp[k].se, acc);
+                                if (valid[k]) st_stream1(oc + (size_t)r * p.W + h * 32, acc);
+                            }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&empty_bar[s]);
             }
         }
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(&empty_bar[s]);
+    }
+
+    // ---- epilogue (consumers): drain the work list of unstageable tiles, then sign off.
+    // Work item n = (tile slot n / per_tile, 32 x 8 pixel block, 8-channel chunk).
+    constexpr int ICH = 8;
+    const int nchunk_c = (p.C + ICH - 1) / ICH;
+    const int per_tile = (TW / 32) * (TH / 8) * nchunk_c;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int got = -1;
+            int n = *reinterpret_cast<volatile int*>(&work->next);
+            for (;;) {
+                const int avail = *reinterpret_cast<volatile int*>(&work->count) * per_tile;
+                if (n >= avail) break;
+                const int old = atomicCAS(&work->next, n, n + 1);
+                if (old == n) { got = n; break; }
+                n = old;
+            }
+            s_item = got;
+        }
+        tma::bar_sync_consumers(Cfg::CONSUMER_WARPS * 32);
+        const int it = s_item;
+        tma::bar_sync_consumers(Cfg::CONSUMER_WARPS * 32);
+        if (it < 0) break;
+        int tile;
+        do {  // the appender stores the tile id right after reserving the slot
+            tile = *reinterpret_cast<volatile int*>(&work->items[it / per_tile]);
+        } while (tile == 0);
+        tile -= 1;
+        int r = it % per_tile;
+        const int chunk = r % nchunk_c; r /= nchunk_c;
+        const int sx = r % (TW / 32), sy = r / (TW / 32);
+        const int ttx = tile % gridDim.x, tty = (tile / gridDim.x) % gridDim.y;
+        const int tb = tile / (gridDim.x * gridDim.y);
+        const int x = ttx * TW + sx * 32 + lane, y = tty * TH + sy * 8 + warp;
+        if (x < p.W && y < p.H)
+            gather_pixel<ICH>(in, flow, out, lin_x, lin_y, p, tb, x, y, chunk * ICH,
+                              min(p.C, chunk * ICH + ICH));
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(&work->exited, 1) == total - 1) {
+            // last CTA of the launch: leave the workspace zeroed for the next launch
+            const int n = *reinterpret_cast<volatile int*>(&work->count);
+            for (int i = 0; i < n; ++i) work->items[i] = 0;
+            work->count = 0;
+            work->next = 0;
+            __threadfence();
+            work->exited = 0;
+        }
     }
 }
 
@@ -408,11 +431,6 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     }
     return fn;
 }
-
-int dsvc_warp_deferred_launch(const float* input, const float* flow, float* out,
-                              const float* lin_x, const float* lin_y, const WarpParams& p,
-                              const DeferredTiles* list, int tile_w, int tile_h, int tiles_x,
-                              int tiles_y, cudaStream_t st);  // warp_gather.cu
 
 template <class Cfg>
 static int launch_cfg(const float* input, const float* flow, float* out, const float* lin_x,
@@ -439,21 +457,37 @@ static int launch_cfg(const float* input, const float* flow, float* out, const f
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((p.W + Cfg::TW - 1) / Cfg::TW, (p.H + Cfg::TH - 1) / Cfg::TH, p.B);
-    const size_t ntiles = (size_t)grid.x * grid.y * grid.z;
-    DeferredTiles* list = nullptr;
-    if (workspace && workspace_bytes >= sizeof(DeferredTiles) + ntiles * sizeof(int) &&
-        aligned16(workspace)) {
-        list = static_cast<DeferredTiles*>(workspace);
-        cudaError_t e = cudaMemsetAsync(&list->count, 0, sizeof(int), st);
-        if (e != cudaSuccess) return (int)e;
+    const int tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW, tiles_y = (p.H + Cfg::TH - 1) / Cfg::TH;
+    const size_t ntiles = (size_t)tiles_x * tiles_y * p.B;
+    if (!workspace || workspace_bytes < sizeof(WarpWork) + ntiles * sizeof(int) || !aligned16(workspace))
+        return -1;  // no work list: the caller uses the gather kernel
+    // channel split: as close as possible to a whole number of waves of resident CTAs
+    static int num_sms = 0, forced_split = -1;
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+            num_sms = DSVC_NUM_SMS;
+        const char* e = getenv("DSVC_TMA_CSPLIT");  // tuning knob
+        forced_split = e ? atoi(e) : 0;
     }
-    warp_fwd_tma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tm, input, flow, out,
-                                                                          lin_x, lin_y, p, list);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || !list) return (int)e;
-    return dsvc_warp_deferred_launch(input, flow, out, lin_x, lin_y, p, list, Cfg::TW, Cfg::TH,
-                                     (int)grid.x, (int)grid.y, st);
+    const double slots = 2.0 * num_sms;  // __launch_bounds__(THREADS, 2)
+    int csplit = 1;
+    double best = 0.0;
+    for (int cs = 1; cs <= 8; cs *= 2) {
+        const int cper = ((p.C + cs - 1) / cs + Cfg::CC - 1) / Cfg::CC * Cfg::CC;
+        if (cs > 1 && (cper < 8 || (long long)p.B * cs > 65535)) break;
+        const double units = (double)ntiles * cs;
+        const double eff = units / (ceil(units / slots) * slots) - 0.01 * (cs - 1);  // flow re-read cost
+        if (eff > best + 1e-9) { best = eff; csplit = cs; }
+    }
+    if (forced_split > 0) csplit = forced_split;
+    const int cper = ((p.C + csplit - 1) / csplit + Cfg::CC - 1) / Cfg::CC * Cfg::CC;
+    if ((long long)p.B * csplit > 65535) return -1;
+    dim3 grid(tiles_x, tiles_y, p.B * csplit);
+    warp_fwd_tma_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
+        tm, input, flow, out, lin_x, lin_y, p, static_cast<WarpWork*>(workspace), csplit, cper);
+    return (int)cudaGetLastError();
 }
 
 // returns -1 when the shape is not eligible (caller uses the gather kernel)

@@ -49,11 +49,24 @@ def _base_grids(device, H, W):
     return g
 
 
-def warp_workspace(device, B, H, W):
-    """Scratch for the staged kernel's deferred-tile list: a fresh tensor from torch's
-    caching allocator (stream-ordered, so concurrent streams never share it)."""
+_ws_cache = {}
+
+
+def warp_workspace(device, B, H, W, private=False):
+    """Work list for the staged kernel (``dsvc_warp_fwd_f32``'s `workspace`): zero-filled
+    once, left zero-filled by every launch.  One buffer per (device, stream) is cached and
+    reused by eager calls (launches on one stream are ordered); ``private=True`` returns
+    a fresh buffer for a caller that binds it into its own launch sequence / CUDA graph."""
     n = _lib.load().dsvc_warp_workspace_bytes(B, H, W)
-    return torch.empty(n, dtype=torch.uint8, device=device)
+    if private or torch.cuda.is_current_stream_capturing():
+        # under a user's graph capture the zero-fill is captured with the launch
+        return torch.zeros(n, dtype=torch.uint8, device=device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.zeros(max(n, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
 
 
 def _scales(H, W):
@@ -101,7 +114,7 @@ def warp_forward(inp, flow, flow_mode=None, algo=None):
     lin_x, lin_y = _base_grids(inp.device, H, W)
     sx, sy, inv_sx, inv_sy = _scales(H, W)
     lib = _lib.load()
-    ws = warp_workspace(inp.device, B, H, W) if (layout == _lib.LAYOUT_NCHW and C >= 8) else None
+    ws = warp_workspace(inp.device, B, H, W) if layout == _lib.LAYOUT_NCHW else None
     with torch.cuda.device(inp.device):
         err = lib.dsvc_warp_fwd_f32(
             inp.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W,

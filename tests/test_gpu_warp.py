@@ -237,3 +237,25 @@ def test_full_size_1080p_properties():
     assert (got - ref).abs().max().item() <= 5e-3  # coordinate rounding ~2e-4 px * gradient
     # checksum property: sum over taps of weights is 1 -> mean preserved for a shift
     assert abs(got.double().mean().item() - ref.double().mean().item()) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["smooth", "stress"])
+def test_tma_worklist_left_zeroed(oracle, kind):
+    """The staged kernel's work list (workspace) is zero before and after every launch,
+    also when every tile is unstageable (stress flow: all tiles go through the list),
+    and back-to-back launches on one workspace are bit-identical."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import _lib, synthetic, warp as W
+    g = torch.Generator().manual_seed(5)
+    B, C, H, Wd = 2, 24, 96, 192
+    inp = torch.randn(B, C, H, Wd, generator=g)
+    flow = (synthetic.smooth_flow if kind == "smooth" else synthetic.stress_flow)(B, H, Wd, g)
+    ref = oracle.torch_warp(inp, flow)
+    x, f = inp.to(_dev()), flow.to(_dev())
+    outs = [d.warp_forward(x, f, flow_mode=_lib.FLOW_TRUE_DIVIDE, algo=_lib.WARP_TMA) for _ in range(3)]
+    torch.cuda.synchronize()
+    ws = W.warp_workspace(x.device, B, H, Wd)
+    assert int(ws.count_nonzero()) == 0
+    assert_warp_close(outs[0], ref, f"worklist {kind}")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    assert torch.equal(outs[0], d.warp_forward(x, f, flow_mode=_lib.FLOW_TRUE_DIVIDE, algo=_lib.WARP_GATHER))
