@@ -65,4 +65,13 @@ __device__ __forceinline__ void st_stream1(float* p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+template <int IMM>
+__device__ __forceinline__ void st_stream1_imm(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0+%2], %1;" ::"l"(p), "f"(v), "n"(IMM) : "memory");
+}
+
+template <int IMM>
+__device__ __forceinline__ void st_hint_imm(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0+%2], %1, %3;" ::"l"(p), "f"(v), "n"(IMM), "l"(pol) : "memory");
+}
 }  // namespace dsvc

@@ -55,7 +55,7 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int W, int H) {
 }
 
 // One thread: output pixel (x, y) of batch item b, channels [c0, cend) -- the direct
-// read-only-path gather (used by the gather kernel and by the staged kernel's work-list epilogue).
+// read-only-path gather (the gather kernel, and the staged kernel for rectangles it cannot stage).
 template <int UNROLL>
 __device__ __forceinline__ void gather_pixel(const float* __restrict__ in,
                                              const float* __restrict__ flow,
@@ -108,14 +108,12 @@ __device__ __forceinline__ void gather_pixel(const float* __restrict__ in,
     }
 }
 
-// Work list of tiles the staged kernel could not stage (bounding box too large).  Lives
-// in the caller's workspace, which is all-zero before and after every launch.
-struct WarpWork {
-    int count;     // tile slots reserved by appenders
-    int next;      // work items claimed so far (items, not tiles)
-    int exited;    // CTAs that have signed off; the last one re-zeroes the list
-    int pad;
-    int items[1];  // tile id + 1 per slot (0 = not yet published)
+// Scheduler state of the persistent staged kernel (warp_persist.cu).  Lives in the caller's
+// workspace, which is all-zero before and after every launch.
+struct WarpSched {
+    int next;    // work units claimed so far
+    int exited;  // CTAs that have run dry; the last one re-zeroes the state
+    int pad[2];
 };
 
 }  // namespace dsvc

@@ -2,10 +2,12 @@
 //
 // Replaces /root/reference/modules.py:25-62 (torch_warp) and its autograd.
 // These kernels read the four taps straight through the read-only path; the
-// shared-memory/TMA-staged forward lives in warp_tma.cu and is preferred when the
+// shared-memory/TMA-staged forward lives in warp_persist.cu and is preferred when the
 // shape allows.  HBM-bound op: one launch reads input + flow once and writes out
 // once (4*B*H*W*(2C+2) algorithmic bytes); coordinates and weights are computed
 // once per pixel and reused for every channel.
+#include <cstdlib>
+
 #include "warp_common.cuh"
 #include "../../include/deepsvc_b200.h"
 
@@ -158,10 +160,10 @@ warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
 
 using namespace dsvc;
 
-int dsvc_warp_fwd_tma_launch(const float* input, const float* flow, float* out,
-                             const float* lin_x, const float* lin_y, const WarpParams& p,
-                             bool force, void* workspace, size_t workspace_bytes,
-                             cudaStream_t st);  // warp_tma.cu
+int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* out,
+                                 const float* lin_x, const float* lin_y, const WarpParams& p,
+                                 bool force, void* workspace, size_t workspace_bytes,
+                                 cudaStream_t st);  // warp_persist.cu
 
 static int warp_args_ok(const void* a, const void* b, const void* c, int B, int C, int H, int W,
                         const void* lx, const void* ly) {
@@ -195,8 +197,8 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
     }
     DSVC_CHECK_ARG(layout == DSVC_LAYOUT_NCHW);
     if (algo == DSVC_WARP_AUTO || algo == DSVC_WARP_TMA) {
-        const int r = dsvc_warp_fwd_tma_launch(input, flow, out, lin_x, lin_y, p,
-                                               algo == DSVC_WARP_TMA, workspace, workspace_bytes, st);
+        const int r = dsvc_warp_fwd_persist_launch(input, flow, out, lin_x, lin_y, p, algo == DSVC_WARP_TMA,
+                                                   workspace, workspace_bytes, st);
         if (r != -1) return r;  // -1: shape not supported by the staged kernel -> gather
         if (algo == DSVC_WARP_TMA) return (int)cudaErrorInvalidValue;
     }
@@ -220,9 +222,7 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
 
 extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
-    // work list: header + one int per tile of the smallest staged tile (32 x 16)
-    const size_t ntiles = (size_t)B * ((W + 31) / 32) * ((H + 15) / 16);
-    return sizeof(WarpWork) + ntiles * sizeof(int) + 16;
+    return sizeof(WarpSched) + 48;  // scheduler state of the persistent staged kernel
 }
 
 extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,

@@ -65,15 +65,15 @@ int dsvc_device_arch(void);
  * bit for bit.  flow is always NCHW [B,2,H,W] (ch0 = dx, ch1 = dy, pixels).
  * input/out: [B,C,H,W] in `layout`.
  *
- * workspace (device, 16-byte aligned, nullable): work list of at least
- * dsvc_warp_workspace_bytes(B, H, W) bytes for the shared-memory/TMA-staged kernel.
- * It MUST be zero-filled before its first use; every launch leaves it zero-filled
- * again, so one buffer can serve any number of launches that are ordered on one
- * stream (two launches that may run concurrently need two buffers).  Tiles whose
- * source bounding box cannot be staged are cut into work items on this list and
- * gathered by all CTAs of the same launch.  Without a workspace DSVC_WARP_AUTO uses
- * the gather kernel and DSVC_WARP_TMA fails with DSVC_ERR_INVALID_ARG.  Results are
- * bit-identical on every path. */
+ * workspace (device, 16-byte aligned, nullable): scheduler state (a work-unit counter)
+ * of at least dsvc_warp_workspace_bytes(B, H, W) bytes for the persistent
+ * shared-memory/TMA-staged kernel.  It MUST be zero-filled before its first use; every
+ * launch leaves it zero-filled again, so one buffer can serve any number of launches
+ * that are ordered on one stream (two launches that may run concurrently need two
+ * buffers).  Tiles whose source bounding box cannot be staged are re-staged as
+ * quadrants or gathered directly inside the same launch.  Without a workspace
+ * DSVC_WARP_AUTO uses the gather kernel and DSVC_WARP_TMA fails with
+ * DSVC_ERR_INVALID_ARG.  Results are bit-identical on every path. */
 int dsvc_warp_fwd_f32(const float* input, const float* flow, float* out,
                       int B, int C, int H, int W,
                       const float* lin_x, const float* lin_y,

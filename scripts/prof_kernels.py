@@ -47,7 +47,7 @@ def main():
     ap.add_argument("--height", type=int, default=1088)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--flow", default="smooth")
+    ap.add_argument("--flow", default="smooth")  # smooth | stress | border | zero | shift | nojitter
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-flush", action="store_true")
     a = ap.parse_args()
@@ -55,7 +55,15 @@ def main():
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     B, H, W = a.batch, a.height, a.width
-    cpu_in = synthetic.make_pframe_inputs(B=B, H=H, W=W, seed=16, flow_kind=a.flow)
+    special = a.flow in ("zero", "shift", "nojitter")
+    cpu_in = synthetic.make_pframe_inputs(B=B, H=H, W=W, seed=16, flow_kind="smooth" if special else a.flow)
+    if a.flow == "zero":
+        cpu_in["flow"].zero_()
+    elif a.flow == "shift":
+        cpu_in["flow"][:, 0] = 5.3
+        cpu_in["flow"][:, 1] = -3.6
+    elif a.flow == "nojitter":
+        cpu_in["flow"] = synthetic.smooth_flow(B, H, W, torch.Generator().manual_seed(3), jitter=0.0)
     d = synthetic.to_device(cpu_in, dev)
     flush = None if a.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     algo = {"auto": _lib.WARP_AUTO, "gather": _lib.WARP_GATHER, "tma": _lib.WARP_TMA}[a.algo]

@@ -37,7 +37,7 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     assert lib.dsvc_warp_fwd_f32(None, None, None, 1, 3, 8, 8, None, None, 1.0, 1.0, 1.0, 1.0,
                                  0, 0, 0, None, 0, None) == 1
-    assert lib.dsvc_warp_workspace_bytes(1, 1088, 1920) >= 4 * 60 * 68
+    assert lib.dsvc_warp_workspace_bytes(1, 1088, 1920) >= 16  # scheduler state
     assert lib.dsvc_gc_fwd_f32(None, None, None, None, None, None, None, None, None, None, 0,
                                None, 0.11, 1e-9, 1, 16, 16, 16, 16, 16, None) == 1
     assert lib.dsvc_reduce_slots(1, 65280) == (65280 + 511) // 512

@@ -239,10 +239,36 @@ def test_full_size_1080p_properties():
     assert abs(got.double().mean().item() - ref.double().mean().item()) < 1e-5
 
 
+@pytest.mark.parametrize("cut", ["x", "y", "xy", "wild_corner"])
+def test_tma_motion_boundary_quadrants(oracle, cut):
+    """Tiles whose bounding box does not fit the staging box because a motion boundary
+    crosses them: the staged kernel re-stages them as quadrants (each side of the boundary
+    fits on its own), or gathers a quadrant that is itself wild.  Bit-identical to the
+    gather kernel, within tolerance of the oracle."""
+    from deepsvc_b200 import synthetic
+    g = torch.Generator().manual_seed(11)
+    B, C, H, Wd = 1, 20, 128, 256
+    inp = torch.randn(B, C, H, Wd, generator=g)
+    flow = torch.randn(B, 2, H, Wd, generator=g) * 0.3
+    ys = torch.arange(H).view(1, H, 1).expand(B, H, Wd)
+    xs = torch.arange(Wd).view(1, 1, Wd).expand(B, H, Wd)
+    if "x" in cut:   # boundary in the middle of every 64-wide tile
+        flow[:, 0] += torch.where((xs % 64) < 32, 30.0, -30.0)
+    if "y" in cut:   # boundary in the middle of every 32-high tile
+        flow[:, 1] += torch.where((ys % 32) < 16, -25.0, 25.0)
+    if cut == "wild_corner":
+        flow[:, :, :16, :32] = synthetic.stress_flow(B, 16, 32, g, sigma=40.0)
+        flow[:, 0, 64:, 128:] += torch.where((xs[:, 64:, 128:] % 64) < 32, 30.0, -30.0)
+    ref = oracle.torch_warp(inp, flow)
+    got = _warp(inp.to(_dev()), flow.to(_dev()), "cpu", "tma")
+    assert_warp_close(got, ref, f"motion boundary {cut}")
+    assert torch.equal(got, _warp(inp.to(_dev()), flow.to(_dev()), "cpu", "gather"))
+
+
 @pytest.mark.parametrize("kind", ["smooth", "stress"])
-def test_tma_worklist_left_zeroed(oracle, kind):
-    """The staged kernel's work list (workspace) is zero before and after every launch,
-    also when every tile is unstageable (stress flow: all tiles go through the list),
+def test_tma_scheduler_state_left_zeroed(oracle, kind):
+    """The staged kernel's scheduler state (workspace) is zero before and after every
+    launch, also when every tile is unstageable (stress flow: every rectangle is gathered),
     and back-to-back launches on one workspace are bit-identical."""
     import deepsvc_b200 as d
     from deepsvc_b200 import _lib, synthetic, warp as W
@@ -256,6 +282,6 @@ def test_tma_worklist_left_zeroed(oracle, kind):
     torch.cuda.synchronize()
     ws = W.warp_workspace(x.device, B, H, Wd)
     assert int(ws.count_nonzero()) == 0
-    assert_warp_close(outs[0], ref, f"worklist {kind}")
+    assert_warp_close(outs[0], ref, f"scheduler {kind}")
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
     assert torch.equal(outs[0], d.warp_forward(x, f, flow_mode=_lib.FLOW_TRUE_DIVIDE, algo=_lib.WARP_GATHER))
