@@ -6,6 +6,7 @@
 // shape allows.  HBM-bound op: one launch reads input + flow once and writes out
 // once (4*B*H*W*(2C+2) algorithmic bytes); coordinates and weights are computed
 // once per pixel and reused for every channel.
+#include <algorithm>
 #include <cstdlib>
 
 #include "warp_common.cuh"
@@ -27,6 +28,123 @@ warp_fwd_nchw_gather(const float* __restrict__ in, const float* __restrict__ flo
     const int c0 = (blockIdx.z - b * nchunk) * cpc;
     if (x >= p.W || y >= p.H) return;
     gather_pixel<UNROLL>(in, flow, out, lin_x, lin_y, p, b, x, y, c0, min(p.C, c0 + cpc));
+}
+
+// ------------------------------------------------------------------ NCHW forward, few channels
+// Frames and SpyNet pyramid levels (C = 3; modules.py:167, video_model.py:37).  With so few
+// channels the per-pixel coordinate and address arithmetic is the cost (the one-pixel-per-
+// thread gather issues ~250 instructions per pixel and is issue-bound at 2.7 TB/s), so this
+// kernel keeps it lean: 32-bit element offsets, taps outside the image read a clamped
+// in-image address with an exactly-zero weight instead of being branched around, a
+// persistent grid strides over 32 x (8*PX) pixel tiles, every thread keeps the 4*C*PX taps of
+// its PX pixels in flight at once and loads the NEXT tile's flow before it gathers the
+// current one.  Results are identical to gather_pixel's on finite inputs.
+template <int C, int PX, int FM>
+__global__ void __launch_bounds__(256)
+warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow,
+                    float* __restrict__ out, const float* __restrict__ lin_x,
+                    const float* __restrict__ lin_y, WarpParams p, unsigned tiles_x,
+                    unsigned tiles_y, unsigned total_tiles) {
+    const unsigned lane = threadIdx.x, wy = threadIdx.y;
+    const unsigned W = p.W, H = p.H, plane = H * W;  // C*H*W < 2^31 (checked by the launcher)
+    float fx[PX], fy[PX];
+    // tile coordinates advance by gridDim.x tiles per iteration without divisions
+    const unsigned step_r = gridDim.x / tiles_x, step_x = gridDim.x - step_r * tiles_x;
+    const unsigned step_b = step_r / tiles_y, step_y = step_r - step_b * tiles_y;
+    struct Tile { unsigned tx, ty, b; };
+    auto advance = [&](Tile& q) {
+        q.tx += step_x;
+        const unsigned cx = q.tx >= tiles_x ? 1u : 0u;
+        q.tx -= cx ? tiles_x : 0u;
+        q.ty += step_y + cx;
+        const unsigned cy = q.ty >= tiles_y ? 1u : 0u;
+        q.ty -= cy ? tiles_y : 0u;
+        q.b += step_b + cy;
+    };
+    auto load_flow = [&](const Tile& q) {
+        const unsigned x = q.tx * 32 + lane, y0 = q.ty * (8 * PX) + wy;
+        const float* fl = flow + (size_t)q.b * 2 * plane;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            const unsigned y = y0 + 8 * j;
+            const unsigned pix = (x < W && y < H) ? y * W + x : 0u;
+            fx[j] = __ldg(fl + pix);
+            fy[j] = __ldg(fl + (pix + plane));
+        }
+    };
+    unsigned t = blockIdx.x;
+    Tile next;
+    {
+        const unsigned r = t / tiles_x;
+        next.tx = t - r * tiles_x;
+        next.b = r / tiles_y;
+        next.ty = r - next.b * tiles_y;
+    }
+    if (t < total_tiles) load_flow(next);
+    for (; t < total_tiles; t += gridDim.x) {
+        const Tile cur = next;
+        const unsigned b = cur.b, x = cur.tx * 32 + lane, y0 = cur.ty * (8 * PX) + wy;
+        float cfx[PX], cfy[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) { cfx[j] = fx[j]; cfy[j] = fy[j]; }
+        advance(next);
+        if (t + gridDim.x < total_tiles) load_flow(next);  // in flight during this tile
+        const float* inb = in + (size_t)b * C * plane;
+        float* outb = out + (size_t)b * C * plane;
+        const float lx = __ldg(lin_x + min(x, W - 1));
+        float wnw[PX], wne[PX], wsw[PX], wse[PX];
+        const float* qn[PX];
+        bool ok[PX];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            const unsigned y = y0 + 8 * j;
+            ok[j] = x < W && y < H;
+            const float ix = source_coord(lx, cfx[j], p.sx, p.inv_sx, FM, (int)W);
+            const float iy = source_coord(__ldg(lin_y + min(y, H - 1)), cfy[j], p.sy, p.inv_sy, FM, (int)H);
+            const Taps tp = make_taps(ix, iy, (int)W, (int)H);
+            // The 2 x 2 footprint always starts at (min(x0, W-2), min(y0, H-2)), so that the four
+            // taps sit at fixed offsets (+1, +W) from one address.  A coordinate on the far border
+            // (x0 = W-1, where the reference skips the outside taps and their weights are exactly
+            // 0) moves its weights one column / row over instead: same products, same order.
+            const bool sx_ = !tp.x1ok, sy_ = !tp.y1ok;
+            const unsigned xb = sx_ ? W - 2 : (unsigned)tp.x0, yb = sy_ ? H - 2 : (unsigned)tp.y0;
+            const float n0 = sx_ ? 0.0f : tp.nw, n1 = sx_ ? tp.nw : tp.ne;  // north row, west / east
+            const float s0 = sx_ ? 0.0f : tp.sw, s1 = sx_ ? tp.sw : tp.se;  // south row
+            wnw[j] = sy_ ? 0.0f : n0;
+            wne[j] = sy_ ? 0.0f : n1;
+            wsw[j] = sy_ ? n0 : s0;
+            wse[j] = sy_ ? n1 : s1;
+            qn[j] = inb + (ok[j] ? yb * W + xb : 0u);
+        }
+        float v[PX][C][4];
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            const float* q = qn[j];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float* qs = q + W;
+                v[j][c][0] = __ldg(q);
+                v[j][c][1] = __ldg(q + 1);
+                v[j][c][2] = __ldg(qs);
+                v[j][c][3] = __ldg(qs + 1);
+                q += plane;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PX; ++j) {
+            if (!ok[j]) continue;
+            float* op = outb + ((y0 + 8 * j) * W + x);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float acc = __fmul_rn(v[j][c][0], wnw[j]);
+                acc = fmaf(v[j][c][1], wne[j], acc);
+                acc = fmaf(v[j][c][2], wsw[j], acc);
+                acc = fmaf(v[j][c][3], wse[j], acc);
+                st_stream1(op, acc);
+                op += plane;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ NHWC forward
@@ -201,6 +319,36 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
                                                    workspace, workspace_bytes, st);
         if (r != -1) return r;  // -1: shape not supported by the staged kernel -> gather
         if (algo == DSVC_WARP_TMA) return (int)cudaErrorInvalidValue;
+    }
+    if (C <= 4 && H >= 2 && W >= 2 && (long long)C * H * W < (1ll << 31)) {
+        // frames / pyramid levels: persistent few-channel kernel, one CTA per resident slot
+        constexpr int PX = 2;
+        const unsigned tiles_x = (W + 31) / 32, tiles_y = (H + 8 * PX - 1) / (8 * PX);
+        const long long total = (long long)tiles_x * tiles_y * B;
+        DSVC_CHECK_ARG(total < (1ll << 31));
+        auto launch = [&](auto kernel) -> int {
+            static int slots = 0;  // per instantiation
+            if (slots == 0) {
+                int dev = 0, sms = 0, per_sm = 0;
+                if (cudaGetDevice(&dev) != cudaSuccess ||
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+                    sms = DSVC_NUM_SMS;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm <= 0)
+                    per_sm = 2;
+                slots = sms * per_sm;
+            }
+            const int grid = (int)std::min<long long>(total, slots);
+            kernel<<<grid, dim3(32, 8), 0, st>>>(input, flow, out, lin_x, lin_y, p, tiles_x, tiles_y, (unsigned)total);
+            return (int)cudaGetLastError();
+        };
+#define DSVC_FEWCH(CN) return flow_mode ? launch(warp_fwd_nchw_fewch<CN, PX, 1>) : launch(warp_fwd_nchw_fewch<CN, PX, 0>)
+        switch (C) {
+            case 1: DSVC_FEWCH(1);
+            case 2: DSVC_FEWCH(2);
+            case 3: DSVC_FEWCH(3);
+            default: DSVC_FEWCH(4);
+        }
+#undef DSVC_FEWCH
     }
     // channel chunk per CTA: enough CTAs to fill the machine, few flow re-reads
     int cpc = C;
