@@ -293,10 +293,13 @@ def run_ours(args):
                 "whole_frame": {"algorithmic_bytes": bytes_alg["total"],
                                 "achieved_gbs": bytes_alg["total"] * args.steps / (ms_local * 1e-3) / 1e9,
                                 "frac_of_peak": bytes_alg["total"] * args.steps / (ms_local * 1e-3) / 1e9 / peak}}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(prof):
+    # DRAM bytes of the same kernel from the committed ncu --set full capture (per launch)
+    prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(prof) and (Hh, Ww, B) == (1088, 1920, 1):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("warp_fwd_feature_bytes_per_launch")
+            t = json.load(open(prof))
+            roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+            roofline["traffic_source"] = t["source"]
         except Exception:
             pass
 

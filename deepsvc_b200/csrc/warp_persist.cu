@@ -54,7 +54,9 @@ struct PersistCfg {
     static constexpr int CHUNK_FLOATS = CC * ROWCHUNK * BW;    // one TMA box [8 rows][CC][BW]
     static constexpr int STAGE_FLOATS = (BHMAX / ROWCHUNK) * CHUNK_FLOATS;
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * sizeof(float);
+    static constexpr int QY_ROWS_DIV = TH > 16 ? 2 : 1;
     static constexpr int NDESC = 2;  // unit descriptors in flight (scout runs ahead)
+    static constexpr int SCOUT_RB = TH / QY_ROWS_DIV;  // scout: rows per batch (flow loads in flight)
     static_assert(TH % CONSUMER_WARPS == 0 && TW % 32 == 0 && BHMAX % ROWCHUNK == 0, "tile shape");
     static constexpr int QX = TW >= 64 ? 2 : 1, QY = 2;  // sub-rectangles of an unstageable tile
     static_assert((TW & (TW - 1)) == 0 && TH % QY == 0 && (TW / QX) % 32 == 0, "sub-rectangles are whole lane groups");
@@ -97,47 +99,61 @@ struct Schedule {
     int total_units;
 };
 
-// Source bounding box of the pixels of rectangle [rx0,rx1) x [ry0,ry1) of the tile at
-// (tx0, ty0): north-west tap positions, warp-reduced (all lanes return the same box).
+// Source coordinates of the pixels of rectangle [rx0,rx1) x [ry0,ry1) of the tile at (tx0, ty0),
+// written to `coords` (tile-relative [y][x], TW wide) for the consumers, and their bounding box
+// (north-west tap positions), warp-reduced (all lanes return the same box).  A lane owns the
+// columns lane, lane + 32, ... of the rectangle (rx0, rx1 are multiples of 32) and walks down
+// the rows RB at a time with all 2*RB flow loads in flight; min / max run on the float
+// coordinates (floor is monotone, so floor(min) = min(floor)).
+template <int TW, int RB>
 __device__ __forceinline__ void scout_bbox(const float* __restrict__ fl, const float* __restrict__ lin_x,
                                            const float* __restrict__ lin_y, const WarpParams& p,
                                            int tx0, int ty0, int rx0, int rx1, int ry0, int ry1,
-                                           int lane, int& mnx, int& mxx, int& mny, int& mxy) {
-    constexpr int U = 16;  // 2*U flow loads in flight per lane
+                                           int lane, float2* __restrict__ coords, int& mnx, int& mxx,
+                                           int& mny, int& mxy) {
     const size_t plane = (size_t)p.H * p.W;
-    const int rw = rx1 - rx0, n = rw * (ry1 - ry0);
-    const int sh = 31 - __clz(rw);  // rectangle widths are powers of two (TW, TW / 2)
-    mnx = INT_MAX; mxx = INT_MIN; mny = INT_MAX; mxy = INT_MIN;
-    for (int i0 = 0; i0 < n; i0 += 32 * U) {
-        float fx[U], fy[U];
+    float lox = 3.0e38f, hix = -1.0f, loy = 3.0e38f, hiy = -1.0f;  // coordinates are in [0, size-1]
+    for (int xx = rx0 + lane; xx < rx1; xx += 32) {
+        const int x = tx0 + xx;
+        const bool xok = x < p.W;
+        const int xc = min(x, p.W - 1);
+        const float lx = __ldg(lin_x + xc);
+        for (int r0 = ry0; r0 < ry1; r0 += RB) {
+            float fx[RB], fy[RB];
+            const float* fp = fl + (size_t)min(ty0 + r0, p.H - 1) * p.W + xc;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int x = tx0 + rx0 + (i & (rw - 1)), y = ty0 + ry0 + (i >> sh);
-            const bool ok = i < n && x < p.W && y < p.H;
-            const size_t pix = ok ? (size_t)y * p.W + x : 0;
-            fx[u] = __ldg(fl + pix);
-            fy[u] = __ldg(fl + plane + pix);
-        }
+            for (int j = 0; j < RB; ++j) {
+                // rows past the rectangle / image re-read the last legal row (discarded below)
+                const float* q = (r0 + j < ry1 && ty0 + r0 + j < p.H) ? fp + (size_t)j * p.W : fp;
+                fx[j] = __ldg(q);
+                fy[j] = __ldg(q + plane);
+            }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * 32 + lane;
-            const int x = tx0 + rx0 + (i & (rw - 1)), y = ty0 + ry0 + (i >> sh);
-            if (i < n && x < p.W && y < p.H) {
-                const float ix = source_coord(__ldg(lin_x + x), fx[u], p.sx, p.inv_sx, p.flow_mode, p.W);
-                const float iy = source_coord(__ldg(lin_y + y), fy[u], p.sy, p.inv_sy, p.flow_mode, p.H);
-                const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);
-                mnx = min(mnx, x0); mxx = max(mxx, x0);
-                mny = min(mny, y0); mxy = max(mxy, y0);
+            for (int j = 0; j < RB; ++j) {
+                const int yy = r0 + j, y = ty0 + yy;
+                if (xok && yy < ry1 && y < p.H) {
+                    const float ix = source_coord(lx, fx[j], p.sx, p.inv_sx, p.flow_mode, p.W);
+                    const float iy = source_coord(__ldg(lin_y + y), fy[j], p.sy, p.inv_sy, p.flow_mode, p.H);
+                    coords[yy * TW + xx] = make_float2(ix, iy);
+                    lox = fminf(lox, ix); hix = fmaxf(hix, ix);
+                    loy = fminf(loy, iy); hiy = fmaxf(hiy, iy);
+                }
             }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+        hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+        hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    }
+    if (hix < 0.0f) {  // no pixel of the rectangle is inside the image
+        mnx = mny = INT_MAX;
+        mxx = mxy = INT_MIN;
+    } else {
+        mnx = (int)floorf(lox); mxx = (int)floorf(hix);
+        mny = (int)floorf(loy); mxy = (int)floorf(hiy);
     }
 }
 
@@ -156,6 +172,7 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     __shared__ __align__(8) uint64_t desc_full[ND];
     __shared__ __align__(8) uint64_t desc_empty[ND];
     __shared__ __align__(16) UnitDesc desc[ND];
+    __shared__ __align__(16) float2 coords[ND][TW * TH];  // per-pixel source coordinates of a unit
 
     // (warp index broadcast from lane 0 so that the compiler treats role branches as warp-uniform)
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
@@ -185,13 +202,20 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
     if (warp == Cfg::SCOUT_WARP) {
         // ------------------------------------------------------------------ scout
         int du = 0;
+        bool have_slot = false;
+        // a descriptor slot (descriptor + coordinate buffer) is written only after every reader
+        // of its previous contents has released it
+        auto acquire = [&]() {
+            if (!have_slot && du >= ND) tma::mbar_wait(dempty0 + 8u * (du % ND), ((du / ND) - 1) & 1);
+            have_slot = true;
+        };
         auto post = [&](const UnitDesc& d) {
             const int slot = du % ND;
-            if (du >= ND) tma::mbar_wait(dempty0 + 8u * slot, ((du / ND) - 1) & 1);
             if (lane == 0) desc[slot] = d;
-            __syncwarp();
+            __syncwarp();  // every lane's coordinate stores precede the release below
             if (lane == 0) tma::mbar_arrive(dfull0 + 8u * slot);
             ++du;
+            have_slot = false;
         };
         for (;;) {
             int u = 0;
@@ -222,7 +246,9 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
             // whole tile and does not fit (the caller then posts the quadrants)
             auto describe = [&](int rx0, int rx1, int ry0, int ry1, bool whole) -> bool {
                 int mnx, mxx, mny, mxy;
-                scout_bbox(fl, lin_x, lin_y, p, d.tx0, d.ty0, rx0, rx1, ry0, ry1, lane, mnx, mxx, mny, mxy);
+                acquire();
+                scout_bbox<TW, Cfg::SCOUT_RB>(fl, lin_x, lin_y, p, d.tx0, d.ty0, rx0, rx1, ry0, ry1, lane,
+                                             coords[du % ND], mnx, mxx, mny, mxy);
                 if (mnx > mxx) return true;  // rectangle entirely outside the image: nothing to do
                 // taps reach x0+1 / y0+1 (clamped to the image); TMA tiled loads need a 16-byte
                 // aligned start along x (an unaligned coordinate raises "illegal instruction")
@@ -253,6 +279,7 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         }
         UnitDesc e{};
         e.mode = UNIT_END;
+        acquire();
         post(e);
         if (lane == 0) {
             // the last scout to run dry leaves the scheduler state zeroed for the next launch
@@ -311,36 +338,31 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         if (threadIdx.x == 0) DSVC_TR(du, 8, clock64());
         tma::mbar_wait(dfull0 + 8u * slot, (du / ND) & 1);
         const UnitDesc d = desc[slot];
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(dempty0 + 8u * slot);  // the descriptor is in registers
-        if (threadIdx.x == 0) DSVC_TR(du, 9, clock64());
         if (d.mode == UNIT_END) break;
         long long tw_full = 0;
         (void)tw_full;
 
-        // per-pixel source coordinates (once per unit, reused for every channel)
+        // per-pixel source coordinates: computed once by the scout, reused for every channel
         float ixs[PPT], iys[PPT];
         bool valid[PPT];
         uint32_t vmask = 0;
-        const float* fl = flow + (size_t)d.b * 2 * plane;
 #pragma unroll
         for (int r = 0; r < RPW; ++r) {
 #pragma unroll
             for (int h = 0; h < XH; ++h) {
                 const int k = r * XH + h;
                 const int xx = h * 32 + lane, yy = warp * RPW + r;
-                const int x = d.tx0 + xx, y = d.ty0 + yy;
-                valid[k] = xx >= d.rx0 && xx < d.rx1 && yy >= d.ry0 && yy < d.ry1 && x < p.W && y < p.H;
-                ixs[k] = iys[k] = 0.0f;
+                valid[k] = xx >= d.rx0 && xx < d.rx1 && yy >= d.ry0 && yy < d.ry1 &&
+                           d.tx0 + xx < p.W && d.ty0 + yy < p.H;
                 vmask |= valid[k] ? 1u << k : 0u;
-                if (valid[k]) {
-                    const size_t pix = (size_t)y * p.W + x;
-                    const float fx = __ldg(fl + pix), fy = __ldg(fl + plane + pix);
-                    ixs[k] = source_coord(__ldg(lin_x + x), fx, p.sx, p.inv_sx, p.flow_mode, p.W);
-                    iys[k] = source_coord(__ldg(lin_y + y), fy, p.sy, p.inv_sy, p.flow_mode, p.H);
-                }
+                const float2 c = valid[k] ? coords[slot][yy * TW + xx] : make_float2(0.0f, 0.0f);
+                ixs[k] = c.x;
+                iys[k] = c.y;
             }
         }
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(dempty0 + 8u * slot);  // descriptor and coordinates are in registers
+        if (threadIdx.x == 0) DSVC_TR(du, 9, clock64());
 
         if (d.mode == UNIT_GATHER) {
             // rectangle whose taps do not fit the staging box: read-only-path gather

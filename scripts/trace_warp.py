@@ -30,7 +30,10 @@ def build():
 
 
 def main():
-    if "--build" in sys.argv or not os.path.isfile(LIB):
+    csrc = os.path.join(ROOT, "deepsvc_b200", "csrc")
+    stale = not os.path.isfile(LIB) or any(
+        os.path.getmtime(f) > os.path.getmtime(LIB) for f in glob.glob(os.path.join(csrc, "*")))
+    if stale or "--build" in sys.argv:
         build()
     if "--build-only" in sys.argv:
         return
