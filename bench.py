@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flow", default="smooth", choices=["smooth", "stress", "border"])
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tma"])
+    ap.add_argument("--branches4", action="store_true",
+                    help="capture the 4-branch DAG (feature | 3-ch warps | mv | res entropy) instead "
+                         "of one graph branch per launch")
     ap.add_argument("--serial", action="store_true",
                     help="capture the frame's 25 launches in serial order instead of as a DAG")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -242,7 +245,7 @@ def run_ours(args):
     models = build_models(dev)
     gpu_in = synthetic.to_device(cpu_in, dev)
     hp = PFrameHotPath(gpu_in, models, warp_algo=algo)
-    hp.capture(dag=not args.serial)
+    hp.capture(dag=False if args.serial else (True if args.branches4 else "wide"))
     bytes_alg = synthetic.pframe_algorithmic_bytes(B, Hh, Ww)
 
     def barrier():
@@ -344,6 +347,9 @@ def run_ours(args):
                        "l2": "inputs larger than L2: 1.26 GB working set per frame vs 126 MB L2, no flush needed",
                        "launch": ("CUDA graph replay of the frame's 25 hot-path launches, "
                                   + ("serial order" if args.serial else
+                                     "captured as their data-dependency DAG (one branch per launch: no "
+                                     "op of the path consumes another's output; joined by bits_finalize)"
+                                     if not args.branches4 else
                                      "captured as their data-dependency DAG (4 branches: feature warp | "
                                      "3-ch warps | mv entropy | res entropy, joined by bits_finalize)")),
                        "bpp_check": bpp},

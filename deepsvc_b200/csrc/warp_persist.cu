@@ -533,23 +533,26 @@ static int launch_persist(const float* input, const float* flow, float* out, con
                               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // per-device set-up (function attributes and SM counts belong to the device, not the process)
+    static unsigned long long attr_set = 0;
+    static int sms_of[64];
+    static int env_split = 0, env_tail_pct = 100;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    if (!((attr_set >> dev) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(warp_fwd_persist_kernel<Cfg>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = DSVC_NUM_SMS;
+        sms_of[dev] = n;
+        if (const char* e2 = getenv("DSVC_WARP_TAIL_SPLIT")) env_split = atoi(e2);  // tuning knobs
+        if (const char* e2 = getenv("DSVC_WARP_TAIL_PCT")) env_tail_pct = atoi(e2);
+        attr_set |= 1ull << dev;
     }
-    static int num_sms = 0, env_split = 0, env_tail_pct = 100;
-    if (num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
-            num_sms = DSVC_NUM_SMS;
-        if (const char* e = getenv("DSVC_WARP_TAIL_SPLIT")) env_split = atoi(e);  // tuning knobs
-        if (const char* e = getenv("DSVC_WARP_TAIL_PCT")) env_tail_pct = atoi(e);
-    }
+    const int num_sms = sms_of[dev];
     const int slots = Cfg::MINB * num_sms;  // __launch_bounds__(THREADS, MINB)
     Schedule sch;
     sch.tiles_x = (p.W + Cfg::TW - 1) / Cfg::TW;
