@@ -5,7 +5,7 @@
 //
 // One persistent CTA per resident slot (2 per SM) pulls work units from a device-side
 // counter.  A unit is a TW x TH tile of output pixels of one batch item and a channel
-// range: whole tiles first, then the last ~one-wave's worth of tiles cut into `tail_split`
+// range: whole tiles first, then the last one-wave's worth of tiles cut into `tail_split` (2)
 // channel ranges, so that all CTAs run dry within a fraction of a tile time (a plain grid
 // of 1020 tiles is 3.45 waves of 296 slots: 14 % of the machine idles in the last wave).
 //
@@ -61,7 +61,7 @@ struct PersistCfg {
     static constexpr int QX = TW >= 64 ? 2 : 1, QY = 2;  // sub-rectangles of an unstageable tile
     static_assert((TW & (TW - 1)) == 0 && TH % QY == 0 && (TW / QX) % 32 == 0, "sub-rectangles are whole lane groups");
     static_assert((BW * 4) % 16 == 0 && (CHUNK_FLOATS * 4) % 128 == 0, "TMA alignment");
-    static_assert(ROW_PITCH % 32 == 0, "row pitch must be a multiple of the 32 banks");
+    static_assert(ROW_PITCH % 16 == 0, "row pitch: a multiple of the 32 banks (or of 16: slightly more conflicts)");
 };
 
 enum : int { UNIT_STAGED = 0, UNIT_GATHER = 1, UNIT_END = 2 };
@@ -560,7 +560,7 @@ static int launch_persist(const float* input, const float* flow, float* out, con
     const long long ntiles = (long long)sch.tiles_x * sch.tiles_y * p.B;
     if (ntiles > (1ll << 28)) return -1;
     // the last `tail` tiles (about one wave) are cut into channel ranges of >= 8 channels
-    int split = env_split > 0 ? env_split : 4;
+    int split = env_split > 0 ? env_split : 2;
     while (split > 1 && p.C / split < 8) split >>= 1;
     const long long tail = std::min<long long>(ntiles, (long long)slots * env_tail_pct / 100);
     sch.tail_split = split;
@@ -627,7 +627,14 @@ int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* o
         case 12: return launch_persist<PersistCfg<128, 8, 160, 24, 1, 5>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         case 13: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         case 14: return launch_persist<PersistCfg<128, 16, 160, 32, 1, 5>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 15: return launch_persist<PersistCfg<64, 16, 80, 32, 1, 6>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 16: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 7>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 17: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 4>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 18: return launch_persist<PersistCfg<64, 16, 80, 32, 1, 8>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 19: return launch_persist<PersistCfg<64, 16, 80, 32, 1, 5>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 20: return launch_persist<PersistCfg<64, 16, 80, 32, 1, 7>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         case 8: return launch_persist<PersistCfg<64, 16, 80, 32, 2, 2>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
-        default: return launch_persist<PersistCfg<64, 16, 80, 32, 2, 4>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 21: return launch_persist<PersistCfg<64, 16, 80, 32, 2, 4>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        default: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
     }
 }

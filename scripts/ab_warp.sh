@@ -1,8 +1,13 @@
 #!/bin/bash
+# A/B of the staged warp kernel's tuning knobs at 1080p C=64 (run under gpurun).
 out=gpurun_out/ab_warp.txt; : > $out
-run() { echo "== $* $EXTRA" >> $out; env "$@" python scripts/prof_kernels.py --what feature --iters 30 $EXTRA 2>&1 | grep "warp_fwd" >> $out; }
+run() { echo "== $* $EXTRA" >> $out; env "$@" python scripts/prof_kernels.py --what feature --iters 40 $EXTRA 2>&1 | grep "warp_fwd" >> $out; }
 EXTRA=""
-run DSVC_WARP_KNOBS=0
-for k in 1 2 3 4 8 10; do run DSVC_WARP_KNOBS=$k; done
-for p in 0 2 3; do run DSVC_TMA_PROMO=$p; done
+run DSVC_TMA_CFG=15 DSVC_WARP_TAIL_SPLIT=2
+run DSVC_TMA_CFG=19 DSVC_WARP_TAIL_SPLIT=2
+run DSVC_TMA_CFG=20 DSVC_WARP_TAIL_SPLIT=2
+run DSVC_TMA_CFG=15 DSVC_WARP_TAIL_SPLIT=2 DSVC_WARP_TAIL_PCT=70
+run DSVC_TMA_CFG=15 DSVC_WARP_TAIL_SPLIT=2 DSVC_WARP_TAIL_PCT=150
+run DSVC_TMA_CFG=15 DSVC_WARP_TAIL_SPLIT=1
+run DSVC_TMA_CFG=13 DSVC_WARP_TAIL_SPLIT=2
 cat $out
