@@ -10,6 +10,7 @@
 #include <type_traits>
 #include <cstdlib>
 
+#include "warp_bwd_common.cuh"
 #include "warp_common.cuh"
 #include "../../include/deepsvc_b200.h"
 
@@ -192,10 +193,9 @@ warp_fwd_nhwc(const float* __restrict__ in, const float* __restrict__ flow,
 }
 
 // ------------------------------------------------------------------ backward (NCHW)
-// One thread per output pixel, all channels: grad_flow is a per-pixel reduction over
-// C kept in registers; grad_input taps are scattered with float reductions
-// (RED.ADD.F32, no return value).  Restates ATen grid_sampler_2d_backward_kernel
-// (bilinear / border / align_corners) followed by the division by sx, sy.
+// One thread per output pixel, all channels (warp_bwd_common.cuh): the general-shape kernel.
+// The bandwidth-critical calls (C >= 8, 16-byte aligned rows) take the staged kernel of
+// warp_bwd_staged.cu, which pre-combines the scatter per tile in shared memory.
 template <bool NEED_GIN, bool NEED_GFLOW>
 __global__ void __launch_bounds__(256)
 warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
@@ -204,75 +204,9 @@ warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
               const float* __restrict__ lin_y, WarpParams p) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
-    const int b = blockIdx.z;
     if (x >= p.W || y >= p.H) return;
-    const size_t plane = (size_t)p.H * p.W;
-    const size_t pix = (size_t)y * p.W + x;
-    const float* fl = flow + (size_t)b * 2 * plane + pix;
-    const float fx = __ldg(fl), fy = __ldg(fl + plane);
-    // unclipped coordinate, then clip_coordinates_set_grad
-    const float fsx = p.flow_mode ? __fdiv_rn(fx, p.sx) : __fmul_rn(fx, p.inv_sx);
-    const float fsy = p.flow_mode ? __fdiv_rn(fy, p.sy) : __fmul_rn(fy, p.inv_sy);
-    float ix = __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(__ldg(lin_x + x), fsx), 1.0f), 0.5f),
-                         (float)(p.W - 1));
-    float iy = __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(__ldg(lin_y + y), fsy), 1.0f), 0.5f),
-                         (float)(p.H - 1));
-    float gx_mult = (float)(p.W - 1) * 0.5f, gy_mult = (float)(p.H - 1) * 0.5f;
-    if (ix <= 0.0f) { ix = 0.0f; gx_mult = 0.0f; }
-    else if (ix >= (float)(p.W - 1)) { ix = (float)(p.W - 1); gx_mult = 0.0f; }
-    if (iy <= 0.0f) { iy = 0.0f; gy_mult = 0.0f; }
-    else if (iy >= (float)(p.H - 1)) { iy = (float)(p.H - 1); gy_mult = 0.0f; }
-    const Taps t = make_taps(ix, iy, p.W, p.H);
-    const float fx0 = (float)t.x0, fy0 = (float)t.y0;
-    const float wx0 = __fsub_rn(fx0 + 1.0f, ix), wx1 = __fsub_rn(ix, fx0);
-    const float wy0 = __fsub_rn(fy0 + 1.0f, iy), wy1 = __fsub_rn(iy, fy0);
-    const int o_nw = t.y0 * p.W + t.x0;
-    const int dx = t.x1ok ? 1 : 0, dy = t.y1ok ? p.W : 0;
-    const bool xe = t.x1ok, ys = t.y1ok, xy = t.x1ok && t.y1ok;
-    const float* gp = gout + (size_t)b * p.C * plane + pix;
-    const float* ip = in + (size_t)b * p.C * plane + o_nw;
-    float* gi = NEED_GIN ? gin + (size_t)b * p.C * plane + o_nw : nullptr;
-    float gix = 0.0f, giy = 0.0f;
-#pragma unroll 4
-    for (int c = 0; c < p.C; ++c) {
-        const float g = __ldg(gp);
-        if (NEED_GIN) {
-            atomicAdd(gi, __fmul_rn(t.nw, g));
-            if (xe) atomicAdd(gi + dx, __fmul_rn(t.ne, g));
-            if (ys) atomicAdd(gi + dy, __fmul_rn(t.sw, g));
-            if (xy) atomicAdd(gi + dy + dx, __fmul_rn(t.se, g));
-            gi += plane;
-        }
-        if (NEED_GFLOW) {
-            const float v_nw = __ldg(ip);
-            gix -= v_nw * wy0 * g;
-            giy -= v_nw * wx0 * g;
-            if (xe) {
-                const float v = __ldg(ip + dx);
-                gix += v * wy0 * g;
-                giy -= v * wx1 * g;
-            }
-            if (ys) {
-                const float v = __ldg(ip + dy);
-                gix -= v * wy1 * g;
-                giy += v * wx0 * g;
-            }
-            if (xy) {
-                const float v = __ldg(ip + dy + dx);
-                gix += v * wy1 * g;
-                giy += v * wx1 * g;
-            }
-            ip += plane;
-        }
-        gp += plane;
-    }
-    if (NEED_GFLOW) {
-        float* gf = gflow + (size_t)b * 2 * plane + pix;
-        const float ggx = __fmul_rn(gx_mult, gix), ggy = __fmul_rn(gy_mult, giy);
-        // autograd of flow / s: grad / s  (CUDA: grad * (1/s))
-        gf[0] = p.flow_mode ? __fdiv_rn(ggx, p.sx) : __fmul_rn(ggx, p.inv_sx);
-        gf[plane] = p.flow_mode ? __fdiv_rn(ggy, p.sy) : __fmul_rn(ggy, p.inv_sy);
-    }
+    bwd_pixel_direct<NEED_GIN, NEED_GFLOW>(gout, in, flow, gin, gflow, lin_x, lin_y, p, blockIdx.z, x, y,
+                                           0, p.C, false);
 }
 
 }  // namespace dsvc
@@ -283,6 +217,10 @@ int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* o
                                  const float* lin_x, const float* lin_y, const WarpParams& p,
                                  bool force, void* workspace, size_t workspace_bytes,
                                  cudaStream_t st);  // warp_persist.cu
+
+int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const float* flow, float* gin,
+                                float* gflow, const float* lin_x, const float* lin_y, const WarpParams& p,
+                                bool force, cudaStream_t st);  // warp_bwd_staged.cu
 
 static int warp_args_ok(const void* a, const void* b, const void* c, int B, int C, int H, int W,
                         const void* lx, const void* ly) {
@@ -376,6 +314,13 @@ extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
     return sizeof(WarpSched) + 48;  // scheduler state of the persistent staged kernel
 }
 
+static int g_bwd_algo = -1;  // DSVC_WARP_BWD_* (tests / profiling; default from $DSVC_BWD_ALGO)
+extern "C" int dsvc_set_warp_bwd_algo(int algo) {
+    DSVC_CHECK_ARG(algo >= 0 && algo <= 2);
+    g_bwd_algo = algo;
+    return 0;
+}
+
 extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,
                                  float* grad_input, float* grad_flow, int B, int C, int H, int W,
                                  const float* lin_x, const float* lin_y, float sx, float sy,
@@ -387,6 +332,15 @@ extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, cons
     if (!grad_input && !grad_flow) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+    // 0 = auto (staged kernel when the shape is eligible), 1 = per-pixel kernel, 2 = staged forced
+    if (g_bwd_algo < 0) { const char* e = getenv("DSVC_BWD_ALGO"); g_bwd_algo = e ? atoi(e) : 0; }
+    const int algo = g_bwd_algo;
+    if (algo != 1) {
+        const int r = dsvc_warp_bwd_staged_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p,
+                                                  algo == 2, st);
+        if (r != -1) return r;
+        if (algo == 2) return (int)cudaErrorInvalidValue;
+    }
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B);
     if (grad_input && grad_flow)
         warp_bwd_nchw<true, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);

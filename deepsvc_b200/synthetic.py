@@ -43,6 +43,17 @@ def border_flow(B, H, W, gen, margin=64, reach=64.0):
     return torch.cat([fx, fy], 1).contiguous()
 
 
+def make_flow(kind, B, H, W, gen):
+    """The three flow families of SURVEY 8d by name: smooth | stress | border."""
+    if kind == "smooth":
+        return smooth_flow(B, H, W, gen)
+    if kind == "stress":
+        return stress_flow(B, H, W, gen)
+    if kind == "border":
+        return border_flow(B, H, W, gen, margin=max(1, min(H, W) // 4), reach=40.0)
+    raise ValueError(f"unknown flow kind {kind!r}")
+
+
 def make_latents(B, C, h, w, gen, tie_frac=0.01, tail_frac=0.001):
     """mu ~ N(0,1); scale = exp(U(ln .05, ln 32)) (about 12 % below the 0.11 bound);
     y = mu + scale * N(0,1) with exact .5 ties and far-tail (likelihood floor) elements."""

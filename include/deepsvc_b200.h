@@ -93,6 +93,17 @@ int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* fl
                       float sx, float sy, float inv_sx, float inv_sy,
                       int flow_mode, int layout, void* stream);
 
+/* Kernel choice of dsvc_warp_bwd_f32 (process-wide; tests and profiling).
+ * DSVC_WARP_BWD_AUTO (0, default, or $DSVC_BWD_ALGO): the shared-memory staged kernel
+ * (per-tile transposed-warp CSR + TMA tensor reduce-add into grad_input, csrc/warp_bwd_staged.cu)
+ * when C >= 8, W % 4 == 0, W >= 64, H >= 16 and the pointers are 16-byte aligned, else the
+ * per-pixel RED.ADD kernel; DSVC_WARP_BWD_DIRECT (1): always the per-pixel kernel;
+ * DSVC_WARP_BWD_STAGED (2): the staged kernel or cudaErrorInvalidValue. */
+#define DSVC_WARP_BWD_AUTO 0
+#define DSVC_WARP_BWD_DIRECT 1
+#define DSVC_WARP_BWD_STAGED 2
+int dsvc_set_warp_bwd_algo(int algo);
+
 /* Number of double partial sums a gc launch over rows x inner elements writes. */
 int dsvc_reduce_slots(int64_t rows, int64_t inner);
 

@@ -95,6 +95,8 @@ def main():
             4 * B * H * W * (3 * 64 + 4))
         rec("warp_bwd C=64 flow-only", timeit(lambda: warp_backward(g, x, f, False, True), a.iters, flush),
             4 * B * H * W * (2 * 64 + 4))
+        rec("warp_bwd C=64 input-only", timeit(lambda: warp_backward(g, x, f, True, False), a.iters, flush),
+            4 * B * H * W * (2 * 64 + 2))
     if want("bwd_frame"):
         x, f = d["ref_frame"], d["flow"]
         g = torch.randn_like(x)

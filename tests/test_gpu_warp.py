@@ -285,3 +285,93 @@ def test_tma_scheduler_state_left_zeroed(oracle, kind):
     assert_warp_close(outs[0], ref, f"scheduler {kind}")
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
     assert torch.equal(outs[0], d.warp_forward(x, f, flow_mode=_lib.FLOW_TRUE_DIVIDE, algo=_lib.WARP_GATHER))
+
+
+# ------------------------------------------------------------------ staged backward (warp_bwd_staged.cu)
+def _bwd_algo(algo):
+    from deepsvc_b200 import _lib
+    _lib.check(_lib.load().dsvc_set_warp_bwd_algo(algo), "dsvc_set_warp_bwd_algo")
+
+
+@pytest.mark.parametrize("need", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("kind", ["smooth", "stress", "border"])
+@pytest.mark.parametrize("shape", [(2, 16, 40, 64), (1, 64, 128, 192), (8, 64, 64, 64), (1, 9, 33, 100),
+                                   (1, 8, 16, 68)])
+def test_backward_staged_vs_stock_torch_cuda(oracle, shape, kind, need):
+    """The staged backward (forced) against autograd of the reference function on the GPU
+    (its GPU branch, modules.py:44-62): gradients within 1e-4 of the tensor's scale."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import _lib, synthetic
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(H * 131 + W + C)
+    inp0 = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow0 = synthetic.make_flow(kind, B, H, W, g).to(_dev())
+    gout = torch.randn(B, C, H, W, generator=g).to(_dev())
+    res = []
+    for fn, algo in ((oracle.torch_warp, _lib.WARP_BWD_AUTO), (d.torch_warp, _lib.WARP_BWD_STAGED)):
+        _bwd_algo(algo)
+        try:
+            inp = inp0.clone().requires_grad_(need[0])
+            flow = flow0.clone().requires_grad_(need[1])
+            fn(inp, flow).backward(gout)
+            res.append((inp.grad, flow.grad))
+        finally:
+            _bwd_algo(_lib.WARP_BWD_AUTO)
+    for a, b, nm in zip(res[1], res[0], ("grad_input", "grad_flow")):
+        if b is None:
+            assert a is None
+            continue
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{nm} {err}"
+
+
+def test_backward_staged_matches_direct_kernel():
+    """Staged and per-pixel kernels on the cfg3 shape (B=8, 64 ch, 256x256): same gradients up
+    to fp32 summation order; grad_input of a constant grad_out sums to the number of taps."""
+    from deepsvc_b200 import _lib, synthetic
+    from deepsvc_b200.warp import warp_backward
+    B, C, H, W = 8, 64, 256, 256
+    g = torch.Generator().manual_seed(5)
+    inp = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow = synthetic.smooth_flow(B, H, W, g).to(_dev())
+    gout = torch.randn(B, C, H, W, generator=g).to(_dev())
+    out = {}
+    for name, algo in (("direct", _lib.WARP_BWD_DIRECT), ("staged", _lib.WARP_BWD_STAGED)):
+        _bwd_algo(algo)
+        try:
+            out[name] = warp_backward(gout, inp, flow, True, True)
+            ones = warp_backward(torch.ones_like(gout), inp, flow, True, False)[0]
+        finally:
+            _bwd_algo(_lib.WARP_BWD_AUTO)
+        # bilinear weights of a pixel sum to 1: every plane of grad_input sums to H*W
+        s = ones.double().sum((2, 3))
+        assert (s - H * W).abs().max().item() <= 1e-3 * H * W, name
+    for a, b, nm in zip(out["staged"], out["direct"], ("grad_input", "grad_flow")):
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{nm} {err}"
+
+
+def test_backward_staged_collapsed_flow_takes_direct_path():
+    """Flow that collapses a whole tile onto one source column (fan-in > MAX_FANIN) must fall
+    back inside the launch and still be right."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import _lib
+    B, C, H, W = 1, 8, 32, 128
+    g = torch.Generator().manual_seed(2)
+    inp0 = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow0 = torch.zeros(B, 2, H, W)
+    flow0[:, 0] = 40.3 - torch.arange(W, dtype=torch.float32)[None, None, :]  # every x -> 40.3
+    flow0 = flow0.to(_dev())
+    gout = torch.randn(B, C, H, W, generator=g).to(_dev())
+    res = []
+    for algo in (_lib.WARP_BWD_DIRECT, _lib.WARP_BWD_STAGED):
+        _bwd_algo(algo)
+        try:
+            inp = inp0.clone().requires_grad_(True)
+            flow = flow0.clone().requires_grad_(True)
+            d.torch_warp(inp, flow).backward(gout)
+            res.append((inp.grad, flow.grad))
+        finally:
+            _bwd_algo(_lib.WARP_BWD_AUTO)
+    for a, b in zip(res[1], res[0]):
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
