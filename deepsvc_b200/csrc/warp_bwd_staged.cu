@@ -106,6 +106,68 @@ __device__ __forceinline__ void sts(uint32_t a, float v) {
 }
 }  // namespace bwd
 
+// A tile whose taps do not fit the staging box (wild flow): direct scatter, channel-outer so
+// that the taps of all the thread's pixels are in flight together.  Not inlined: the staged
+// path keeps its registers (the coordinates are recomputed here).
+template <bool NEED_GIN>
+__device__ __noinline__ void bwd_tile_direct(const float* __restrict__ gout, const float* __restrict__ in,
+                                             const float* __restrict__ flow, float* __restrict__ gin,
+                                             float* __restrict__ gflow, const float* __restrict__ lin_x,
+                                             const float* __restrict__ lin_y, const WarpParams& p, int b,
+                                             int tx0, int ty0, int c_begin, int c_end, bool acc_gflow) {
+    using namespace bwd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t plane = (size_t)p.H * p.W;
+    BwdCoord bc[PPT];
+    bool valid[PPT];
+    int o_nw[PPT], dxg[PPT], dyg[PPT];
+    float gx[PPT], gy[PPT];
+    const float* fl = flow + (size_t)b * 2 * plane;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const int x = tx0 + (k & 1) * 32 + lane, y = ty0 + warp * 2 + (k >> 1);
+        valid[k] = x < p.W && y < p.H;
+        const int xc = min(x, p.W - 1), yc = min(y, p.H - 1);
+        const size_t pix = (size_t)yc * p.W + xc;
+        bc[k] = bwd_coord(__ldg(lin_x + xc), __ldg(lin_y + yc), __ldg(fl + pix), __ldg(fl + plane + pix), p);
+        o_nw[k] = bc[k].t.y0 * p.W + bc[k].t.x0;
+        dxg[k] = bc[k].t.x1ok ? 1 : 0;
+        dyg[k] = bc[k].t.y1ok ? p.W : 0;
+        gx[k] = gy[k] = 0.0f;
+    }
+    const size_t pix0 = (size_t)(ty0 + warp * 2) * p.W + tx0 + lane;
+    for (int c = c_begin; c < c_end; ++c) {
+        const size_t cb = (size_t)(b * p.C + c) * plane;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            if (!valid[k]) continue;
+            const float g = __ldg(gout + cb + pix0 + (size_t)(k >> 1) * p.W + (k & 1) * 32);
+            if (NEED_GIN) {
+                float* gi = gin + cb + o_nw[k];
+                atomicAdd(gi, __fmul_rn(bc[k].t.nw, g));
+                if (dxg[k]) atomicAdd(gi + 1, __fmul_rn(bc[k].t.ne, g));
+                if (dyg[k]) atomicAdd(gi + dyg[k], __fmul_rn(bc[k].t.sw, g));
+                if (dxg[k] && dyg[k]) atomicAdd(gi + dyg[k] + 1, __fmul_rn(bc[k].t.se, g));
+            }
+            if (gflow) {
+                const float* ip = in + cb + o_nw[k];
+                const float v_nw = __ldg(ip), v_ne = __ldg(ip + dxg[k]);
+                const float v_sw = __ldg(ip + dyg[k]), v_se = __ldg(ip + dyg[k] + dxg[k]);
+                const float tx = fmaf(bc[k].wy1, v_se - v_sw, bc[k].wy0 * (v_ne - v_nw));
+                const float ty = fmaf(bc[k].wx1, v_se - v_ne, bc[k].wx0 * (v_sw - v_nw));
+                gx[k] = fmaf(tx, g, gx[k]);
+                gy[k] = fmaf(ty, g, gy[k]);
+            }
+        }
+    }
+    if (gflow) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+            if (valid[k])
+                store_gflow(gflow, p, b, pix0 + (size_t)(k >> 1) * p.W + (k & 1) * 32, bc[k], gx[k], gy[k], acc_gflow);
+    }
+}
+
 // grid.x = tiles * csplit; unit u -> tile u / csplit, channel range (u % csplit) * cper ...
 template <bool NEED_GIN>
 __global__ void __launch_bounds__(bwd::THREADS, 2)
@@ -114,7 +176,7 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
                        const float* __restrict__ in, const float* __restrict__ flow,
                        float* __restrict__ gin, float* __restrict__ gflow,
                        const float* __restrict__ lin_x, const float* __restrict__ lin_y, WarpParams p,
-                       int tiles_x, int tiles_y, int csplit, int cper) {
+                       int tiles_x, int tiles_y, int csplit, int cper, int perm_mul) {
     using namespace bwd;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);          // NS x [in box | grad_out tile]
@@ -276,13 +338,12 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
                 if (dxs[k] && dys[k]) put(e_nw[k] + BW + 1, bc[k].t.se);
             }
             __syncthreads();
-            // the thread's share: 16 consecutive pairs.  Lane l of warp w takes share 32 w + (5 l mod 32):
-            // neighbouring lanes then sit ~23 destination elements (and source pixels) apart -- an odd
-            // stride over the 32 banks instead of ~4.6 (5-way conflicts).  A destination element
+            // the thread's share: 16 consecutive pairs (lane l of warp w takes share 32 w + (m l mod 32);
+            // m = 1: other odd multipliers were measured and change nothing).  A destination element
             // whose run of pairs crosses a share boundary is summed piecewise: the pieces go to the
             // thread's private head / tail slot and are added to the (zeroed) out-box with
             // shared-memory atomics after the loop; whole runs are stored.
-            const int share = warp * 32 + ((lane * 5) & 31);
+            const int share = warp * 32 + ((lane * perm_mul) & 31);
             const int s = SHARE * share, e = min(SHARE * (share + 1), total);
             npairs = max(e - s, 0);
             uint32_t el_before = 0xffffffffu, el_after = 0xffffffffu, el_first = 0u;
@@ -325,17 +386,8 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
         __syncthreads();  // the pair scratch is dead: the load stages may be overwritten
     }
 
-    if (!staged) {
-        // bounding box too large: per-pixel direct scatter (CTA-uniform branch)
-#pragma unroll 1
-        for (int k = 0; k < PPT; ++k) {
-            if (!valid[k]) continue;
-            const int x = tx0 + (k & 1) * 32 + lane, y = ty0 + warp * 2 + (k >> 1);
-            if (gflow)
-                bwd_pixel_direct<NEED_GIN, true>(gout, in, flow, gin, gflow, lin_x, lin_y, p, b, x, y, c_begin, c_end, acc_gflow);
-            else
-                bwd_pixel_direct<NEED_GIN, false>(gout, in, flow, gin, gflow, lin_x, lin_y, p, b, x, y, c_begin, c_end, false);
-        }
+    if (!staged) {  // CTA-uniform
+        bwd_tile_direct<NEED_GIN>(gout, in, flow, gin, gflow, lin_x, lin_y, p, b, tx0, ty0, c_begin, c_end, acc_gflow);
         return;
     }
 
@@ -417,11 +469,14 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
                     acc = fmaf(pw[j0 + u], gv[u], acc);
-                    sts_i<OOFF>(pd[j0 + u], acc);                      // sink unless the pair ends a run
-                    acc = (lastmask >> (j0 + u)) & 1u ? 0.0f : acc;
+                    const bool ends = (lastmask >> (j0 + u)) & 1u;
+                    if (ends) sts_i<OOFF>(pd[j0 + u], acc);  // (predicated store, no branch)
+                    acc = ends ? 0.0f : acc;
                 }
             }
-            // pieces of runs shared with the neighbouring shares (same thread wrote the slots)
+            // pieces of runs shared with the neighbouring shares (same thread wrote the slots).
+            // (Completing a run cut once inside the warp by shuffle + plain store instead was
+            // measured: 964 vs 943 us, the extra registers cost more than the atomics.)
             if (lastmask & (1u << 16)) red_shared(head_dst + OOFF, lds_i<OOFF>(ob_head));
             if (lastmask & (1u << 17)) red_shared(tail_dst + OOFF, lds_i<OOFF>(ob_head + 4u * THREADS));
         }
@@ -509,12 +564,14 @@ int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const flo
         const cudaError_t e = cudaMemsetAsync(gflow, 0, (size_t)p.B * 2 * p.H * p.W * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
+    static int perm_mul = 0;
+    if (perm_mul == 0) { const char* e = getenv("DSVC_BWD_PERM"); perm_mul = e ? (atoi(e) | 1) : 1; }
     const unsigned grid = (unsigned)(ntiles * csplit);
     if (gin)
         warp_bwd_staged_kernel<true><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(
-            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper);
+            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper, perm_mul);
     else
         warp_bwd_staged_kernel<false><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(
-            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper);
+            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper, perm_mul);
     return (int)cudaGetLastError();
 }
