@@ -16,6 +16,19 @@
 
 namespace dsvc {
 
+// The staged warp kernels configure their SMs for the maximum shared-memory carve-out.  A kernel
+// that prefers another L1 / shared-memory split cannot become resident on such an SM until it
+// drains, so the path's short kernels ask for the same carve-out (once per kernel and device)
+// and can run next to the persistent feature warp instead of queueing behind it.
+template <class K>
+inline void prefer_max_shared_carveout(K kernel) {
+    static unsigned long long done = 0;  // one flag per device (per instantiation)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || ((done >> dev) & 1ull)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    done |= 1ull << dev;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -475,6 +475,8 @@ extern "C" int dsvc_gc_fwd_f32(const float* x, const float* scales, const float*
     cudaStream_t st = (cudaStream_t)stream;
     const bool vec = gc_vec_ok(a, rows);
     dim3 grid((unsigned)cdiv(inner, (long long)kGcThreads * kGcVec), (unsigned)rows);
+    prefer_max_shared_carveout(gc_fwd_kernel<true>);
+    prefer_max_shared_carveout(gc_fwd_kernel<false>);
     if (vec) gc_fwd_kernel<true><<<grid, kGcThreads, 0, st>>>(a);
     else gc_fwd_kernel<false><<<grid, kGcThreads, 0, st>>>(a);
     DSVC_RETURN_LAST();
@@ -509,6 +511,7 @@ extern "C" int dsvc_eb_fwd_f32(const float* z, const float* noise, const float* 
     if (B == 0 || C == 0 || S == 0) return 0;
     DSVC_CHECK_ARG((long long)B * S < (1ll << 31) && cdiv((long long)B * S, kEbThreads) <= 65535);
     dim3 grid((unsigned)C, (unsigned)cdiv((long long)B * S, kEbThreads));
+    prefer_max_shared_carveout(eb_fwd_kernel);
     eb_fwd_kernel<<<grid, kEbThreads, 0, (cudaStream_t)stream>>>(
         z, noise, params, outputs, likelihood, z_hat, bits_partials, lik_bound, B, C, S);
     DSVC_RETURN_LAST();
@@ -530,6 +533,7 @@ extern "C" int dsvc_bits_finalize_f64(const double* partials, const int32_t* seg
                                       const double* scales, double* out, int nseg, void* stream) {
     DSVC_CHECK_ARG(partials && seg_offsets && scales && out && nseg >= 0);
     if (nseg == 0) return 0;
+    prefer_max_shared_carveout(bits_finalize_kernel);
     bits_finalize_kernel<<<nseg, 256, 0, (cudaStream_t)stream>>>(partials, seg_offsets, scales, out);
     DSVC_RETURN_LAST();
 }

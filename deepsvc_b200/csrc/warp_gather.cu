@@ -277,6 +277,7 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
                         per_sm = 2;
                     slots = sms * per_sm;
                 }
+                prefer_max_shared_carveout(kernel);
                 const int grid = (int)std::min<long long>(total, slots);
                 kernel<<<grid, dim3(32, 8), 0, st>>>(input, flow, out, lin_x, lin_y, p, tiles_x, tiles_y, (unsigned)total);
                 return (int)cudaGetLastError();

@@ -39,8 +39,12 @@
 
 namespace dsvc {
 
-template <int TW_, int TH_, int BW_, int BHMAX_, int CC_, int STAGES_, int MINB_ = 2>
+template <int TW_, int TH_, int BW_, int BHMAX_, int CC_, int STAGES_, int MINB_ = 2, int MAXREG_ = 96>
 struct PersistCfg {
+    // registers per thread: 96 = what __launch_bounds__(320, 2) gave; 72 leaves 19 K registers per SM
+    // free, so that the frame's short launches (48-reg few-channel warps, entropy kernels) can be
+    // resident next to the two persistent CTAs instead of queueing behind them
+    static constexpr int MAXREG = MAXREG_;
     static constexpr int TW = TW_, TH = TH_, BW = BW_, BHMAX = BHMAX_, CC = CC_, STAGES = STAGES_;
     static constexpr int MINB = MINB_;  // resident CTAs per SM the kernel is compiled for
     static constexpr int CONSUMER_WARPS = 8;
@@ -158,7 +162,7 @@ __device__ __forceinline__ void scout_bbox(const float* __restrict__ fl, const f
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
+__global__ void __maxnreg__(Cfg::MAXREG)
 warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in,
                         const float* __restrict__ flow, float* __restrict__ out,
                         const float* __restrict__ lin_x, const float* __restrict__ lin_y,
@@ -634,7 +638,10 @@ int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* o
         case 19: return launch_persist<PersistCfg<64, 16, 80, 32, 1, 5>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         case 20: return launch_persist<PersistCfg<64, 16, 80, 32, 1, 7>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         case 8: return launch_persist<PersistCfg<64, 16, 80, 32, 2, 2>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 22: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6, 2, 72>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 23: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6, 2, 80>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         case 21: return launch_persist<PersistCfg<64, 16, 80, 32, 2, 4>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
-        default: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        case 24: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+        default: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6, 2, 72>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
     }
 }
