@@ -31,6 +31,9 @@ SIGNATURES = {
     "dsvc_warp_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dsvc_warp_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                   c_float, c_float, c_float, c_float, c_int, c_int, _P]),
+    "dsvc_warp_fused_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
+                                    c_float, c_float, c_float, c_float, c_int, _P]),
+    "dsvc_warp_fused_slots": (c_int, [c_int, c_int, c_int]),
     "dsvc_set_warp_bwd_algo": (c_int, [c_int]),
     "dsvc_reduce_slots": (c_int, [c_int64, c_int64]),
     "dsvc_gc_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P,

@@ -1,0 +1,84 @@
+"""Fusions on either side of the few-channel warps (inference only).
+
+``spynet_level_warp`` replaces the three statements of one SpyNet level
+(``modules.py:163-168``)::
+
+    flow_up = bilinearupsacling(flow) * 2.0
+    warped  = torch_warp(im2, flow_up)
+
+and ``warp_with_mse`` the motion-compensation pair of ``video_model.py:37-38``::
+
+    warped_frame = torch_warp(ref_frame, recon_mv)
+    warp_loss    = torch.mean((warped_frame - curr_frame).pow(2))
+
+Each is one launch of ``dsvc_warp_fused_f32`` (``csrc/warp_fused.cu``).  Neither is
+differentiable: training keeps the unfused drop-in ops.  No CPU path.
+"""
+import torch
+
+from . import _lib
+from . import warp as _warp
+from .entropy import bits_finalize
+
+
+_finalize_consts = {}
+
+
+def _check(name, *ts):
+    for t in ts:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError(f"deepsvc_b200.{name}: contiguous fp32 CUDA tensors required (no CPU fallback)")
+        if t.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError(f"deepsvc_b200.{name}: inference-only fusion (use the unfused ops for training)")
+
+
+def _launch(inp, flow, flow_coarse, flow_up, target, partials, out):
+    B, C, H, W = inp.shape
+    if C > 4:
+        raise RuntimeError("deepsvc_b200 fused warps: C <= 4 (frames, SpyNet pyramid levels)")
+    lin_x, lin_y = _warp._base_grids(inp.device, H, W)
+    sx, sy, inv_sx, inv_sy = _warp._scales(H, W)
+    with torch.cuda.device(inp.device):
+        err = _lib.load().dsvc_warp_fused_f32(
+            inp.data_ptr(), _lib.ptr(flow), _lib.ptr(flow_coarse), _lib.ptr(flow_up), _lib.ptr(target),
+            _lib.ptr(partials), out.data_ptr(), B, C, H, W, lin_x.data_ptr(), lin_y.data_ptr(),
+            sx, sy, inv_sx, inv_sy, _warp._flow_mode, _lib.stream_ptr(inp.device))
+    _lib.check(err, "dsvc_warp_fused_f32")
+
+
+def spynet_level_warp(im2: torch.Tensor, flow: torch.Tensor):
+    """(flow_up [B,2,H,W], warped [B,C,H,W]) from im2 [B,C,H,W] and the previous level's
+    flow [B,2,H/2,W/2] (``modules.py:163-168``)."""
+    _check("spynet_level_warp", im2, flow)
+    B, C, H, W = im2.shape
+    if flow.shape != (B, 2, H // 2, W // 2) or H % 2 or W % 2:
+        raise RuntimeError("deepsvc_b200.spynet_level_warp: flow must be [B,2,H/2,W/2] of an even-sized image")
+    flow_up = torch.empty(B, 2, H, W, dtype=torch.float32, device=im2.device)
+    out = torch.empty_like(im2)
+    if im2.numel():
+        _launch(im2, None, flow, flow_up, None, None, out)
+    return flow_up, out
+
+
+def warp_with_mse(ref_frame: torch.Tensor, flow: torch.Tensor, curr_frame: torch.Tensor):
+    """(warped_frame, warp_loss) of ``video_model.py:37-38``; warp_loss is a 0-d fp64 device
+    tensor (fixed-order sum, bit-identical reruns)."""
+    _check("warp_with_mse", ref_frame, flow, curr_frame)
+    B, C, H, W = ref_frame.shape
+    if flow.shape != (B, 2, H, W) or curr_frame.shape != ref_frame.shape:
+        raise RuntimeError("deepsvc_b200.warp_with_mse: shape mismatch")
+    dev = ref_frame.device
+    n = _lib.load().dsvc_warp_fused_slots(B, H, W)
+    partials = torch.empty(n, dtype=torch.float64, device=dev)
+    out = torch.empty_like(ref_frame)
+    _launch(ref_frame, flow, None, None, curr_frame, partials, out)
+    key = (dev, n, ref_frame.numel())
+    consts = _finalize_consts.get(key)
+    if consts is None:  # built once per shape: no host-to-device copy on the hot path
+        consts = (torch.tensor([0, n], dtype=torch.int32, device=dev),
+                  torch.full((1,), 1.0 / ref_frame.numel(), dtype=torch.float64, device=dev))
+        _finalize_consts[key] = consts
+    return out, bits_finalize(partials, consts[0], consts[1])[0]
+
+
+__all__ = ["spynet_level_warp", "warp_with_mse"]

@@ -93,6 +93,21 @@ int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* fl
                       float sx, float sy, float inv_sx, float inv_sy,
                       int flow_mode, int layout, void* stream);
 
+/* Fusions around the few-channel (C <= 4) warps -- SURVEY.md 8f-3, inference only.
+ * Exactly one of `flow` [B,2,H,W] and `flow_coarse` [B,2,H/2,W/2] is given.
+ *  - flow_coarse: the SpyNet level of modules.py:163-168.  flow_up [B,2,H,W] is written
+ *    with bilinearupsacling(flow_coarse) * 2.0 (F.interpolate x2, bilinear,
+ *    align_corners=False; modules.py:107-112) and `out` = torch_warp(input, flow_up).
+ *  - target [B,C,H,W] (nullable): video_model.py:37-38.  sq_partials
+ *    [dsvc_warp_fused_slots(B,H,W)] receives per-CTA sums of (out - target)^2 in a fixed
+ *    order; dsvc_bits_finalize_f64 with scale 1/(B*C*H*W) turns them into warp_loss. */
+int dsvc_warp_fused_f32(const float* input, const float* flow, const float* flow_coarse,
+                        float* flow_up, const float* target, double* sq_partials, float* out,
+                        int B, int C, int H, int W, const float* lin_x, const float* lin_y,
+                        float sx, float sy, float inv_sx, float inv_sy, int flow_mode,
+                        void* stream);
+int dsvc_warp_fused_slots(int B, int H, int W);
+
 /* Kernel choice of dsvc_warp_bwd_f32 (process-wide; tests and profiling).
  * DSVC_WARP_BWD_AUTO (0, default, or $DSVC_BWD_ALGO): the shared-memory staged kernel
  * (per-tile transposed-warp CSR + TMA tensor reduce-add into grad_input, csrc/warp_bwd_staged.cu)

@@ -68,6 +68,19 @@ def torch_warp(tensorInput: torch.Tensor, tensorFlow: torch.Tensor) -> torch.Ten
                          padding_mode="border", align_corners=True)
 
 
+def spynet_level(im2: torch.Tensor, flow: torch.Tensor):
+    """One SpyNet level's warp input (``modules.py:107-112,163-168``): (flow_up, warped)."""
+    flow_up = F.interpolate(flow, (flow.size(2) * 2, flow.size(3) * 2), mode="bilinear",
+                            align_corners=False) * 2.0
+    return flow_up, torch_warp(im2, flow_up)
+
+
+def warp_and_loss(ref_frame: torch.Tensor, flow: torch.Tensor, curr_frame: torch.Tensor):
+    """``video_model.py:37-38``: (warped_frame, warp_loss)."""
+    warped = torch_warp(ref_frame, flow)
+    return warped, torch.mean((warped - curr_frame).pow(2))
+
+
 def bits_from_likelihoods(likelihoods: torch.Tensor) -> torch.Tensor:
     """Total bits of one likelihood tensor: ``log(l).sum() / -ln 2``
     (``video_model.py:39-42`` before the division by the pixel count)."""
@@ -155,6 +168,6 @@ def pframe_hotpath(inputs: dict, models: dict, training: bool = False) -> dict:
     return out
 
 
-__all__ = ["torch_warp", "bits_from_likelihoods", "make_entropy_models", "codec_entropy_forward",
+__all__ = ["torch_warp", "spynet_level", "warp_and_loss", "bits_from_likelihoods", "make_entropy_models", "codec_entropy_forward",
            "pframe_hotpath", "get_scale_table", "EntropyBottleneck", "GaussianConditional",
            "LowerBound", "ste_round"]

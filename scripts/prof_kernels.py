@@ -102,6 +102,27 @@ def main():
         g = torch.randn_like(x)
         rec("warp_bwd C=3 flow-only", timeit(lambda: warp_backward(g, x, f, False, True), a.iters, flush),
             4 * B * H * W * (2 * 3 + 4))
+    if want("fused"):
+        import torch.nn.functional as F
+        import deepsvc_b200 as dsvc
+        with torch.no_grad():
+            for k in (1, 2, 3):  # SpyNet levels 1..3 warp with the upsampled flow of the level below
+                img = d["pyr_img"][k]
+                h, w = img.shape[2], img.shape[3]
+                coarse = d["pyr_flow"][k][:, :, ::2, ::2].contiguous()
+                def unfused():
+                    fu = F.interpolate(coarse, (h, w), mode="bilinear", align_corners=False) * 2.0
+                    return fu, warp_forward(img, fu)
+                nb = 4 * B * h * w * (2 * 3 + 2) + 4 * B * h * w * 2 // 4
+                rec(f"spynet level {h}x{w} unfused", timeit(unfused, a.iters, flush), nb)
+                rec(f"spynet level {h}x{w} fused", timeit(lambda: dsvc.spynet_level_warp(img, coarse), a.iters, flush), nb)
+            ref, fl, cur = d["ref_frame"], d["flow"], torch.rand_like(d["ref_frame"])
+            def unfused2():
+                wv = warp_forward(ref, fl)
+                return wv, torch.mean((wv - cur).pow(2))
+            nb = 4 * B * H * W * (3 * 3 + 2)
+            rec("frame warp + mse unfused", timeit(unfused2, a.iters, flush), nb)
+            rec("frame warp + mse fused", timeit(lambda: dsvc.warp_with_mse(ref, fl, cur), a.iters, flush), nb)
     if want("gc") or want("eb"):
         import deepsvc_b200 as dsvc
         gc = dsvc.GaussianConditional(None).to(dev).eval()

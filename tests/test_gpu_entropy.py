@@ -250,3 +250,45 @@ def test_full_size_1080p_checksum(oracle):
     assert torch.equal(y_hat2, y_hat)
     assert torch.equal(sym.float() + md, y_hat)
     assert int(idx.min()) >= 0 and int(idx.max()) <= 63
+
+
+@pytest.mark.parametrize("hw", [(16, 28), (68, 120)])
+def test_iframe_codec_shapes_f4(oracle, hw):
+    """the I-frame codec (ICIP2020ResB, image_model.py:440-488) calls the same ops
+    at M = 320 (10 slices x 32 channels) and N = 192 hyper-latent channels.  y_hat / z_hat
+    bit-exact, bits within 1e-4 relative, for the eval path and the fused bit-sum path."""
+    import math
+    import deepsvc_b200 as dsvc
+    from deepsvc_b200 import synthetic
+    dev = torch.device("cuda:0")
+    h, w = hw
+    g = torch.Generator().manual_seed(320 + h)
+    y, scales, means = synthetic.make_latents(1, 320, h, w, g)
+    z = torch.randn(1, 192, max(h // 4, 1), max(w // 4, 1), generator=g) * 3.0
+    eb_o, gc_o = oracle.make_entropy_models(192, seed=192)
+    eb_o.eval(), gc_o.eval()
+    eb = dsvc.EntropyBottleneck(192)
+    eb.load_state_dict(eb_o.state_dict(), strict=False)
+    eb, gc = eb.to(dev).eval(), dsvc.GaussianConditional(None).to(dev).eval()
+    bits_ref = bits_got = 0.0
+    with torch.no_grad():
+        _, zl_ref = eb_o(z)
+        off = eb_o._get_medians()
+        zh_ref = oracle.ste_round(z - off) + off
+        zh, zl, zpart = eb.forward_fused(z.to(dev))
+        assert torch.equal(zh.cpu(), zh_ref)
+        bits_ref += torch.log(zl_ref).sum().item()
+        bits_got += torch.log(zl).sum().item()
+        fused = zpart.sum().item()
+        for y_s, s_s, m_s in zip(y.chunk(10, 1), scales.chunk(10, 1), means.chunk(10, 1)):
+            assert y_s.shape[1] == 32
+            _, lik_ref = gc_o(y_s, s_s, m_s)
+            yh_ref = oracle.ste_round(y_s - m_s) + m_s
+            yh, lik, part = gc.forward_fused(y_s.to(dev), s_s.to(dev), m_s.to(dev))
+            assert torch.equal(yh.cpu(), yh_ref)
+            bits_ref += torch.log(lik_ref).sum().item()
+            bits_got += torch.log(lik).sum().item()
+            fused += part.sum().item()
+    assert abs(bits_got - bits_ref) <= 1e-4 * abs(bits_ref)
+    assert abs(fused - bits_ref) <= 1e-4 * abs(bits_ref)
+    assert math.isfinite(fused)

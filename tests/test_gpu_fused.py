@@ -1,0 +1,66 @@
+"""the fused few-channel warps against the oracle's restatement of the reference
+statements they replace (modules.py:163-168, video_model.py:37-38)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("where", ["cpu", "cuda"])
+@pytest.mark.parametrize("shape", [(1, 3, 32, 56), (2, 3, 136, 240), (1, 3, 2, 2), (1, 1, 34, 66), (1, 3, 1088, 1920)])
+def test_spynet_level_warp(oracle, shape, where):
+    import deepsvc_b200 as d
+    from deepsvc_b200 import synthetic
+    B, C, H, W = shape
+    if where == "cpu" and H * W > 300 * 300:
+        pytest.skip("full size: GPU oracle only")
+    g = torch.Generator().manual_seed(H + W)
+    im2 = torch.rand(B, C, H, W, generator=g)
+    flow = synthetic.smooth_flow(B, max(H // 2, 1), max(W // 2, 1), g, sigma=3.0) if H >= 32 else \
+        torch.randn(B, 2, H // 2, W // 2, generator=g)
+    odev = _dev() if where == "cuda" else torch.device("cpu")
+    d.set_flow_arithmetic(where)
+    try:
+        fu_ref, w_ref = oracle.spynet_level(im2.to(odev), flow.to(odev))
+        fu, w = d.spynet_level_warp(im2.to(_dev()), flow.to(_dev()))
+        # the unfused drop-in on the fused kernel's own flow_up is bit-identical
+        assert torch.equal(d.torch_warp(im2.to(_dev()), fu), w)
+    finally:
+        d.set_flow_arithmetic("cuda")
+    fu_ref, w_ref = fu_ref.to(_dev()), w_ref.to(_dev())
+    assert (fu - fu_ref).abs().max().item() <= 1e-6 * max(1.0, fu_ref.abs().max().item())
+    assert (w - w_ref).abs().max().item() <= 1e-5 * max(1.0, w_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["smooth", "border"])
+@pytest.mark.parametrize("shape", [(1, 3, 64, 96), (2, 3, 100, 132), (1, 3, 1088, 1920)])
+def test_warp_with_mse(oracle, shape, kind):
+    import deepsvc_b200 as d
+    from deepsvc_b200 import synthetic
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(H * 3 + W)
+    ref = torch.rand(B, C, H, W, generator=g).to(_dev())
+    cur = torch.rand(B, C, H, W, generator=g).to(_dev())
+    flow = synthetic.make_flow(kind, B, H, W, g).to(_dev())
+    w_ref, l_ref = oracle.warp_and_loss(ref, flow, cur)
+    w, l = d.warp_with_mse(ref, flow, cur)
+    assert torch.equal(w, d.torch_warp(ref, flow))
+    assert (w - w_ref).abs().max().item() <= 1e-5
+    assert abs(float(l) - float(l_ref)) <= 1e-5 * float(l_ref)
+    assert float(d.warp_with_mse(ref, flow, cur)[1]) == float(l)  # fixed-order sum
+
+
+def test_fused_ops_refuse_training_and_cpu():
+    import deepsvc_b200 as d
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        d.spynet_level_warp(x, torch.zeros(1, 2, 4, 4))
+    xg = x.to(_dev())
+    with pytest.raises(RuntimeError):
+        d.spynet_level_warp(xg, torch.zeros(1, 2, 4, 4, device=_dev(), requires_grad=True))
+    with pytest.raises(RuntimeError):
+        d.spynet_level_warp(torch.rand(1, 8, 8, 8, device=_dev()), torch.zeros(1, 2, 4, 4, device=_dev()))
