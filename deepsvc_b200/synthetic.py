@@ -19,6 +19,11 @@ SEED = 16  # the reference's default seed (utils.py:16)
 MV_CH, RES_CH, FEAT_CH, NUM_SLICES = 64, 96, 64, 8
 
 
+def get_scale_table(lo=0.11, hi=256.0, levels=64):
+    """The reference's scale table (``image_model.py:18-25``: SCALES_MIN/MAX/LEVELS)."""
+    return torch.exp(torch.linspace(math.log(lo), math.log(hi), levels))
+
+
 def smooth_flow(B, H, W, gen, sigma=4.0, jitter=0.25, scale=1.0):
     """SpyNet-like flow: N(0, sigma^2) px on a 1/16 grid, bilinearly upsampled x16
     (``modules.py:107-120,163``), plus per-pixel jitter."""

@@ -375,3 +375,36 @@ def test_backward_staged_collapsed_flow_takes_direct_path():
             _bwd_algo(_lib.WARP_BWD_AUTO)
     for a, b in zip(res[1], res[0]):
         assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+
+
+def test_full_size_4k_forward_and_backward_properties(oracle):
+    """BASELINE config 5 size (2176x3840, 64 ch = 2.14 GB per tensor): forward against the stock
+    torch CUDA branch of the reference function on a smooth flow, and two size-independent
+    backward properties of the staged kernel (plane sums of grad_input for a constant grad_out;
+    grad_flow against stock autograd on a 16-channel slice)."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import synthetic
+    from deepsvc_b200.warp import warp_backward
+    dev = _dev()
+    H, W = 2176, 3840
+    g = torch.Generator().manual_seed(4)
+    flow = synthetic.smooth_flow(1, H, W, g).to(dev)
+    inp = torch.randn(1, 64, H, W, generator=g).to(dev)
+    out = d.torch_warp(inp, flow)
+    ref = oracle.torch_warp(inp, flow)
+    assert (out - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+    del ref, out
+    torch.cuda.empty_cache()
+    gin, _ = warp_backward(torch.ones_like(inp), inp, flow, True, False)
+    s = gin.double().sum((2, 3))
+    assert (s - H * W).abs().max().item() <= 1e-3 * H * W
+    del gin
+    torch.cuda.empty_cache()
+    x16 = inp[:, :16].contiguous().requires_grad_(True)
+    f = flow.clone().requires_grad_(True)
+    go = torch.randn(1, 16, H, W, generator=g).to(dev)
+    oracle.torch_warp(x16, f).backward(go)
+    gi_ref, gf_ref = x16.grad, f.grad
+    gi, gf = warp_backward(go, x16.detach(), flow, True, True)
+    assert (gi - gi_ref).abs().max().item() <= 1e-4 * max(1.0, gi_ref.abs().max().item())
+    assert (gf - gf_ref).abs().max().item() <= 1e-4 * max(1.0, gf_ref.abs().max().item())
