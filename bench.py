@@ -58,9 +58,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 40)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "codec"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "codec"],
                     help="cfg2 (default, the headline line): 1080p P-frame forward path; cfg3: training "
                          "frame-step (B=8, 256x256, forward + backward), a secondary line")
+    ap.add_argument("--gop", type=int, default=32, help="cfg4: GOP size (32 = BASELINE, 12 = test_video.py:22)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
     return ap.parse_args()
@@ -452,6 +453,60 @@ def run_cfg3(args):
         torch.distributed.destroy_process_group()
 
 
+def run_cfg4(args):
+    """Secondary line: BASELINE configs[3] -- 7 independent 1080p sequences of 96 frames, cut into
+    (sequence, GOP) jobs and assigned to the ranks by shard.assign_jobs (static LPT, no data-path
+    collective).  STRONG scaling: the job list is fixed, every rank replays the frame graph once
+    per P-frame of its jobs; time = max over ranks on the device."""
+    import torch
+    from deepsvc_b200 import _lib, shard, synthetic
+    from deepsvc_b200.hotpath import PFrameHotPath
+    rank, local_rank, world = shard.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for --impl ours)")
+    _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    jobs = shard.make_gop_jobs([96] * 7, args.gop)
+    assignment = shard.assign_jobs(jobs, world)
+    mine = assignment[rank]
+    cpu_in = synthetic.make_pframe_inputs(B=B, H=H, W=W, seed=16 + rank)
+    hp = PFrameHotPath(synthetic.to_device(cpu_in, dev), build_models(dev))
+    hp.capture()
+    for _ in range(10):
+        hp.replay()
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local_rank])
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        ev0.record()
+        for job in mine:                 # GOPs are independent; P-frames inside one are serial
+            for _ in range(job.p_frames):
+                hp.replay()
+        ev1.record()
+        torch.cuda.synchronize(dev)
+    ms_local = ev0.elapsed_time(ev1)
+    ms = shard.max_over_ranks(ms_local, dev)
+    total = sum(j.p_frames for j in jobs)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "1080p P-frames/sec (warp+entropy path), 7 x 96-frame sequences sharded by GOP",
+            "value": total / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": total, "warmup": 10,
+            "ms_per_step": ms / total, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4: 7 sequences x 96 frames at 1920x1088, GOP {args.gop}: {len(jobs)} (sequence, GOP) "
+                                   f"jobs = {total} P-frames, static LPT assignment, no data-path collective",
+                       "jobs_per_rank": [len(a) for a in assignment],
+                       "p_frames_per_rank": [sum(j.p_frames for j in a) for a in assignment],
+                       "balance": shard.balance(assignment)},
+            "clocks": sampler.summary()}), flush=True)
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local_rank])
+        torch.distributed.destroy_process_group()
+
+
 def run_codec(args):
     """Secondary line: the symbol pipeline of one coded 1080p P-frame --
     image_model.py:201-257 for both codecs: EntropyBottleneck.compress(z), then per slice
@@ -519,6 +574,8 @@ def main():
         run_reference(args)
     elif args.workload == "cfg3":
         run_cfg3(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
     elif args.workload == "codec":
         run_codec(args)
     else:

@@ -83,10 +83,10 @@ def main():
             4 * B * H * W * (2 * 64 + 2))
     if want("frame"):
         x, f = d["ref_frame"], d["flow"]
-        rec("warp_fwd C=3", timeit(lambda: warp_forward(x, f), a.iters, flush), 4 * B * H * W * 8)
+        rec("warp_fwd C=3", timeit(lambda: warp_forward(x, f, algo=algo), a.iters, flush), 4 * B * H * W * 8)
     if want("spynet"):
         for x, f in zip(d["pyr_img"], d["pyr_flow"]):
-            rec(f"warp_fwd C=3 {x.shape[2]}x{x.shape[3]}", timeit(lambda: warp_forward(x, f), a.iters, flush),
+            rec(f"warp_fwd C=3 {x.shape[2]}x{x.shape[3]}", timeit(lambda: warp_forward(x, f, algo=algo), a.iters, flush),
                 4 * B * x.shape[2] * x.shape[3] * 8)
     if want("bwd_feature"):
         x, f = d["feature"], d["flow"]
