@@ -9,7 +9,7 @@ from . import _lib, ans
 from .warp import torch_warp, warp_forward, warp_backward, set_flow_arithmetic, set_warp_algorithm
 from .entropy import (EntropyBottleneck, EntropyModel, GaussianConditional, LowerBound, ste_round,
                       bits_finalize, bpp_scale)
-from .fused import spynet_level_warp, warp_with_mse
+from .fused import mc_blend, spynet_level_warp, warp_with_mse
 from .patch import patch_reference, swap_entropy_models, unpatch_reference
 
 __version__ = "0.1.0"
@@ -17,4 +17,4 @@ __version__ = "0.1.0"
 __all__ = ["torch_warp", "warp_forward", "warp_backward", "set_flow_arithmetic",
            "set_warp_algorithm", "EntropyBottleneck", "EntropyModel", "GaussianConditional",
            "LowerBound", "ste_round", "bits_finalize", "bpp_scale", "patch_reference",
-           "unpatch_reference", "swap_entropy_models", "spynet_level_warp", "warp_with_mse"]
+           "unpatch_reference", "swap_entropy_models", "spynet_level_warp", "warp_with_mse", "mc_blend"]

@@ -81,4 +81,18 @@ def warp_with_mse(ref_frame: torch.Tensor, flow: torch.Tensor, curr_frame: torch
     return out, bits_finalize(partials, consts[0], consts[1])[0]
 
 
-__all__ = ["spynet_level_warp", "warp_with_mse"]
+def mc_blend(w: torch.Tensor, warped: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
+    """``w * warped + (1 - w) * pred`` (``modules.py:436``) in one pass, bit-identical to the
+    reference's expression."""
+    _check("mc_blend", w, warped, pred)
+    if not (w.shape == warped.shape == pred.shape):
+        raise RuntimeError("deepsvc_b200.mc_blend: shape mismatch")
+    out = torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        err = _lib.load().dsvc_blend_f32(w.data_ptr(), warped.data_ptr(), pred.data_ptr(), out.data_ptr(),
+                                         w.numel(), _lib.stream_ptr(w.device))
+    _lib.check(err, "dsvc_blend_f32")
+    return out
+
+
+__all__ = ["spynet_level_warp", "warp_with_mse", "mc_blend"]

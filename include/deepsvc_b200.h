@@ -108,6 +108,12 @@ int dsvc_warp_fused_f32(const float* input, const float* flow, const float* flow
                         void* stream);
 int dsvc_warp_fused_slots(int B, int H, int W);
 
+/* out = weight * warped + (1 - weight) * pred over n contiguous floats: the motion-compensation
+ * blend of modules.py:436 (`w * warped + (1 - w) * self.out_conv(up_out)`) in one pass,
+ * same order of fp32 operations as the reference's expression (bit-identical). */
+int dsvc_blend_f32(const float* weight, const float* warped, const float* pred, float* out,
+                   int64_t n, void* stream);
+
 /* Kernel choice of dsvc_warp_bwd_f32 (process-wide; tests and profiling).
  * DSVC_WARP_BWD_AUTO (0, default, or $DSVC_BWD_ALGO): the shared-memory staged kernel
  * (per-tile transposed-warp CSR + TMA tensor reduce-add into grad_input, csrc/warp_bwd_staged.cu)

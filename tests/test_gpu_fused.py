@@ -64,3 +64,18 @@ def test_fused_ops_refuse_training_and_cpu():
         d.spynet_level_warp(xg, torch.zeros(1, 2, 4, 4, device=_dev(), requires_grad=True))
     with pytest.raises(RuntimeError):
         d.spynet_level_warp(torch.rand(1, 8, 8, 8, device=_dev()), torch.zeros(1, 2, 4, 4, device=_dev()))
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 64, 96), (2, 3, 33, 47), (1, 3, 1088, 1920), (1, 1, 1, 3)])
+def test_mc_blend_bit_identical(shape):
+    """modules.py:436: w * warped + (1 - w) * pred, bit-identical to the torch expression."""
+    import deepsvc_b200 as d
+    g = torch.Generator().manual_seed(sum(shape))
+    w = torch.rand(shape, generator=g).to(_dev())
+    a = torch.randn(shape, generator=g).to(_dev())
+    b = torch.randn(shape, generator=g).to(_dev())
+    assert torch.equal(d.mc_blend(w, a, b), w * a + (1 - w) * b)
+    # an unaligned view takes the scalar path
+    wv, av, bv = (t.reshape(-1)[1:].contiguous()[1:] for t in (w, a, b))
+    wv, av, bv = (t.reshape(-1)[1:] for t in (w, a, b))
+    assert torch.equal(d.mc_blend(wv, av, bv), wv * av + (1 - wv) * bv)
