@@ -528,6 +528,8 @@ def run_codec(args):
         gc.update_scale_table(synthetic.get_scale_table())
     nsym = sum(d[f"{n}_y"].numel() + d[f"{n}_z"].numel() for n in ("mv", "res"))
 
+    streams = {}
+
     def frame():
         nbytes = 0
         for name in ("mv", "res"):
@@ -539,8 +541,27 @@ def run_codec(args):
                                      d[f"{name}_means"].chunk(8, 1)):
                 sym, idx, _ = gc.quantize_and_index(y_s, s_s, m_s)
                 enc.encode_with_indexes(sym, idx, tables)
-            nbytes += len(enc.flush()) + sum(len(zs) for zs in z_strings)
+            streams[name] = (z_strings, enc.flush())
+            nbytes += len(streams[name][1]) + sum(len(zs) for zs in z_strings)
         return nbytes
+
+    def decode_frame():
+        """image_model.py:259-302: z, then slice by slice build_indexes -> rANS decode -> dequantize."""
+        ok = True
+        for name in ("mv", "res"):
+            eb, gc = models[name]
+            z_strings, y_string = streams[name]
+            eb.decompress(z_strings, d[f"{name}_z"].shape[-2:])
+            tables = gc._cdf_tables()
+            dec = ans.RansDecoder()
+            dec.set_stream(y_string)
+            for y_s, s_s, m_s in zip(d[f"{name}_y"].chunk(8, 1), d[f"{name}_scales"].chunk(8, 1),
+                                     d[f"{name}_means"].chunk(8, 1)):
+                idx = gc.build_indexes(s_s)
+                rv = torch.from_numpy(dec.decode_stream_array(idx, tables)).reshape(s_s.shape).to(dev)
+                y_hat = gc.dequantize(rv, m_s)
+            ok = ok and bool(torch.equal(y_hat, torch.round(y_s - m_s) + m_s))  # last slice round trip
+        return ok
 
     for _ in range(max(2, min(args.warmup, 5))):
         nbytes = frame()
@@ -551,6 +572,13 @@ def run_codec(args):
         frame()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    roundtrip = decode_frame()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        decode_frame()
+    torch.cuda.synchronize()
+    dt_dec = time.perf_counter() - t0
     print(json.dumps({
         "metric": "coded 1080p P-frames/sec (symbol pipeline: quantise+index on GPU, rANS on host)",
         "value": steps / dt, "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": 5,
@@ -558,7 +586,9 @@ def run_codec(args):
         "config": {"workload": f"{args.width}x{args.height} P-frame, both codecs, {nsym} symbols per frame, "
                                "16 slice launches + 2 EntropyBottleneck.compress, two rANS streams",
                    "bytes_per_frame": nbytes, "timing": "host wall clock around synchronised frames (the host coder is the bound)",
-                   "msymbols_per_s": nsym * steps / dt / 1e6}}), flush=True)
+                   "msymbols_per_s": nsym * steps / dt / 1e6,
+                   "decode": {"value": steps / dt_dec, "unit": "frames/s", "ms_per_step": dt_dec / steps * 1e3,
+                              "msymbols_per_s": nsym * steps / dt_dec / 1e6, "round_trip_exact": roundtrip}}}), flush=True)
 
 
 def main():

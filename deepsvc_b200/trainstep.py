@@ -73,6 +73,7 @@ class TrainStepHotPath:
         self.pixels = B * H * W
         self.params = [p for name in ("mv", "res") for p in models[name][0].parameters() if p.requires_grad]
         self._graph = None
+        self._streams = None
         self.loss = None
         self.bpp = None
 
@@ -81,26 +82,43 @@ class TrainStepHotPath:
         return [self.inp[k] for k in LEAVES] + list(self.inp["pyr_flow"])
 
     def forward(self):
-        """Returns (warp outputs in cotangent order, bpp loss, {name: bpp})."""
+        """Returns (warp outputs in cotangent order, bpp loss, {name: bpp}).
+
+        The four independent parts of the path (feature warp | 3-ch warps | mv entropy | res
+        entropy) are issued on four side streams forked from the current one; autograd runs
+        each backward node on its forward stream, so a captured step is a DAG, not a chain."""
         d = self.inp
-        outs = [torch_warp(img, fl) for img, fl in zip(d["pyr_img"], d["pyr_flow"])]  # modules.py:167
-        outs.append(torch_warp(d["ref_frame"], d["flow"]))                            # video_model.py:37
-        outs.append(torch_warp(d["feature"], d["flow"]))                              # modules.py:429
+        dev = d["feature"].device
+        main = torch.cuda.current_stream(dev)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(dev) for _ in range(4)]
+        s_feat, s_w3, s_mv, s_res = self._streams
+        for st in self._streams:
+            st.wait_stream(main)
         scale = -1.0 / (math.log(2) * self.pixels)
-        bpp, loss = {}, None
-        for name in ("mv", "res"):
-            eb, gc = self.models[name]
-            _, z_lik, _ = eb.forward_fused(d[f"{name}_z"], training=True, noise=d[f"{name}_noise_z"])
-            ys = d[f"{name}_y"].chunk(NUM_SLICES, 1)
-            ss = d[f"{name}_scales"].chunk(NUM_SLICES, 1)
-            ms = d[f"{name}_means"].chunk(NUM_SLICES, 1)
-            ns = d[f"{name}_noise_y"].chunk(NUM_SLICES, 1)
-            liks = []
-            for y_s, s_s, m_s, n_s in zip(ys, ss, ms, ns):                         # image_model.py:164-190
-                liks.append(gc.forward_fused(y_s, s_s, m_s, training=True, noise=n_s)[1])
-            y_lik = torch.cat(liks, 1)                                              # image_model.py:191
-            bpp[name] = (torch.log(y_lik).sum() + torch.log(z_lik).sum()) * scale   # video_model.py:39-42
-            loss = bpp[name] if loss is None else loss + bpp[name]
+        with torch.cuda.stream(s_feat):
+            feat = torch_warp(d["feature"], d["flow"])                                # modules.py:429
+        with torch.cuda.stream(s_w3):
+            outs = [torch_warp(img, fl) for img, fl in zip(d["pyr_img"], d["pyr_flow"])]  # modules.py:167
+            outs.append(torch_warp(d["ref_frame"], d["flow"]))                        # video_model.py:37
+        outs.append(feat)
+        bpp = {}
+        for name, st in (("mv", s_mv), ("res", s_res)):
+            with torch.cuda.stream(st):
+                eb, gc = self.models[name]
+                _, z_lik, _ = eb.forward_fused(d[f"{name}_z"], training=True, noise=d[f"{name}_noise_z"])
+                ys = d[f"{name}_y"].chunk(NUM_SLICES, 1)
+                ss = d[f"{name}_scales"].chunk(NUM_SLICES, 1)
+                ms = d[f"{name}_means"].chunk(NUM_SLICES, 1)
+                ns = d[f"{name}_noise_y"].chunk(NUM_SLICES, 1)
+                liks = []
+                for y_s, s_s, m_s, n_s in zip(ys, ss, ms, ns):                     # image_model.py:164-190
+                    liks.append(gc.forward_fused(y_s, s_s, m_s, training=True, noise=n_s)[1])
+                y_lik = torch.cat(liks, 1)                                          # image_model.py:191
+                bpp[name] = (torch.log(y_lik).sum() + torch.log(z_lik).sum()) * scale   # video_model.py:39-42
+        for st in self._streams:
+            main.wait_stream(st)
+        loss = bpp["mv"] + bpp["res"]
         return outs, loss, bpp
 
     def _backward(self, outs, loss):
