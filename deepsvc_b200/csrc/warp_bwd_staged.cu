@@ -227,10 +227,10 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
     if (lane == 0) { red_i[warp][0] = mnx; red_i[warp][1] = mxx; red_i[warp][2] = mny; red_i[warp][3] = mxy; }
     // zero the tap counts and both out-boxes (elements no tap lands on stay zero for every channel)
-    for (int i = tid; i < NE; i += THREADS) {
-        cursor[i] = 0;
-        outbox[i] = 0.0f;
-        outbox[OB_FLOATS + i] = 0.0f;
+    for (int i = tid; i < NE / 4; i += THREADS) {
+        reinterpret_cast<int4*>(cursor)[i] = make_int4(0, 0, 0, 0);
+        reinterpret_cast<float4*>(outbox)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        reinterpret_cast<float4*>(outbox + OB_FLOATS)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     __syncthreads();
 #pragma unroll
@@ -552,13 +552,15 @@ int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const flo
     const int tiles_x = (p.W + bwd::TW - 1) / bwd::TW, tiles_y = (p.H + bwd::TH - 1) / bwd::TH;
     const long long ntiles = (long long)tiles_x * tiles_y * p.B;
     if (ntiles > (1ll << 24)) return -1;
-    // few tiles: cut the channels in ranges so that the machine is filled a few times over
+    // fewer tiles than resident CTAs: cut the channels in ranges.  Not beyond that: the per-tile
+    // set-up (CSR build, ~17 us) is repeated per range -- measured at 8x64x256x256 (512 tiles):
+    // 1 range 280 us, 2 ranges 314 us, 4 ranges 337 us although 512 tiles are only 1.7 waves
     const int slots = 2 * sms_of[dev];
     int csplit = 1;
     static int env_split = -1;
     if (env_split < 0) { const char* e = getenv("DSVC_BWD_CSPLIT"); env_split = e ? atoi(e) : 0; }
     if (env_split > 0) csplit = env_split;
-    else while (ntiles * csplit < 3ll * slots && p.C / (csplit * 2) >= 16) csplit *= 2;
+    else while (ntiles * csplit < (long long)slots && p.C / (csplit * 2) >= 16) csplit *= 2;
     const int cper = (p.C + csplit - 1) / csplit;
     if (gflow && csplit > 1) {
         const cudaError_t e = cudaMemsetAsync(gflow, 0, (size_t)p.B * 2 * p.H * p.W * sizeof(float), st);

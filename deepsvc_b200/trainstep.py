@@ -74,6 +74,9 @@ class TrainStepHotPath:
         self.params = [p for name in ("mv", "res") for p in models[name][0].parameters() if p.requires_grad]
         self._graph = None
         self._streams = None
+        # leaf gradients are accumulated on the side streams on purpose (see forward())
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self.loss = None
         self.bpp = None
 
