@@ -181,7 +181,7 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);          // NS x [in box | grad_out tile]
     float* outbox = stages + NS * STAGE_FLOATS;                  // 2 x ([BH][BW] + private slots)
-    int* cursor = reinterpret_cast<int*>(outbox + 2 * OB_FLOATS);  // [NE] counts -> offsets -> ends
+    int* cursor = reinterpret_cast<int*>(outbox + 2 * OB_FLOATS);  // [NE] tap counts -> first-pair offsets
     uint2* pairs = reinterpret_cast<uint2*>(stages);             // [<= 4096] (weight, e << 10 | q), scratch
     __shared__ __align__(8) uint64_t full_bar[NS];
     __shared__ int red_i[8][4];
@@ -262,13 +262,16 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     int npairs = 0;
     uint32_t quad_s[QPT], quad_g[QPT];  // out-box byte offset (or ~0) / element offset in the plane
     if (NEED_GIN && staged) {
+        int rank[PPT][4];
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             if (!valid[k]) continue;
-            atomicAdd(&cursor[e_nw[k]], 1);
-            if (dxs[k]) atomicAdd(&cursor[e_nw[k] + 1], 1);
-            if (dys[k]) atomicAdd(&cursor[e_nw[k] + BW], 1);
-            if (dxs[k] && dys[k]) atomicAdd(&cursor[e_nw[k] + BW + 1], 1);
+            // the returned count is the tap's rank inside its destination element: kept, so that
+            // the fill below needs no second pass of atomics (integer ATOMS run at 2 cycles per lane)
+            rank[k][0] = atomicAdd(&cursor[e_nw[k]], 1);
+            if (dxs[k]) rank[k][1] = atomicAdd(&cursor[e_nw[k] + 1], 1);
+            if (dys[k]) rank[k][2] = atomicAdd(&cursor[e_nw[k] + BW], 1);
+            if (dxs[k] && dys[k]) rank[k][3] = atomicAdd(&cursor[e_nw[k] + BW + 1], 1);
         }
         __syncthreads();
         // the thread's 16-byte quads of the out-box (<= QPT of the bh x ceil(bw / 4) the box spans)
@@ -323,19 +326,19 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
                 reinterpret_cast<int4*>(cursor)[tid * (EPT / 4) + v] = make_int4(o[0], o[1], o[2], o[3]);
             }
             __syncthreads();
-            // fill: pairs land in destination order (order inside one destination is arbitrary)
+            // fill: pairs land in destination order (inside one destination in the order the counting
+            // atomics were served)
 #pragma unroll
             for (int k = 0; k < PPT; ++k) {
                 if (!valid[k]) continue;
                 const uint32_t q = (uint32_t)((warp * 2 + (k >> 1)) * TW + (k & 1) * 32 + lane);
-                auto put = [&](int e, float w) {
-                    const int slot = atomicAdd(&cursor[e], 1);
-                    pairs[slot] = make_uint2(__float_as_uint(w), ((uint32_t)e << 10) | q);
+                auto put = [&](int e, float w, int r) {  // cursor[e] = first pair of element e
+                    pairs[cursor[e] + r] = make_uint2(__float_as_uint(w), ((uint32_t)e << 10) | q);
                 };
-                put(e_nw[k], bc[k].t.nw);
-                if (dxs[k]) put(e_nw[k] + 1, bc[k].t.ne);
-                if (dys[k]) put(e_nw[k] + BW, bc[k].t.sw);
-                if (dxs[k] && dys[k]) put(e_nw[k] + BW + 1, bc[k].t.se);
+                put(e_nw[k], bc[k].t.nw, rank[k][0]);
+                if (dxs[k]) put(e_nw[k] + 1, bc[k].t.ne, rank[k][1]);
+                if (dys[k]) put(e_nw[k] + BW, bc[k].t.sw, rank[k][2]);
+                if (dxs[k] && dys[k]) put(e_nw[k] + BW + 1, bc[k].t.se, rank[k][3]);
             }
             __syncthreads();
             // the thread's share: 16 consecutive pairs (lane l of warp w takes share 32 w + (m l mod 32);
