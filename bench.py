@@ -242,6 +242,7 @@ def run_ours(args):
     _lib.load()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_bound = shard.bind_to_gpu_numa_node(local_rank) if world > 1 else False
     Hh, Ww = args.height, args.width
     algo = {"auto": _lib.WARP_AUTO, "gather": _lib.WARP_GATHER, "tma": _lib.WARP_TMA}[args.algo]
 
@@ -330,7 +331,8 @@ def run_ours(args):
         e2e = {"value": world * n_e / (e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": sess.h2d_bytes, "d2h_bytes_per_step": sess.d2h_bytes,
                "steps": n_e, "ms_per_step": e_ms / n_e,
-               "api": "deepsvc_b200.hotpath.HostSession.process (pinned host tensors in / out)"}
+               "api": "deepsvc_b200.hotpath.HostSession.process (pinned host tensors in / out)",
+               "cpu_affinity": "GPU-local NUMA node (NVML)" if numa_bound else "inherited"}
         del sess
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on this box's host cores

@@ -79,6 +79,26 @@ def init_distributed(backend: str = None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> bool:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `local_rank`, so that
+    pinned host buffers (first touch) and the copy threads live on the GPU's own NUMA node.
+    Matters for the host-buffer path at 8 ranks per box; a no-op where NVML cannot say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Max of a per-rank scalar (device-side time of the slowest rank)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
