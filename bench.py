@@ -55,6 +55,9 @@ def parse():
                          "of one graph branch per launch")
     ap.add_argument("--serial", action="store_true",
                     help="capture the frame's 25 launches in serial order instead of as a DAG")
+    ap.add_argument("--fuse-frame-warp", action="store_true",
+                    help="variant: the 3-ch frame warp rides on the 64-ch feature warp's launch (same flow; "
+                         "24 launches per frame, an edit of DeepSVC.forward rather than a drop-in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 40)")
@@ -249,7 +252,7 @@ def run_ours(args):
     cpu_in = synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16 + rank, flow_kind=args.flow)
     models = build_models(dev)
     gpu_in = synthetic.to_device(cpu_in, dev)
-    hp = PFrameHotPath(gpu_in, models, warp_algo=algo)
+    hp = PFrameHotPath(gpu_in, models, warp_algo=algo, fuse_frame_warp=args.fuse_frame_warp)
     hp.capture(dag=False if args.serial else (True if args.branches4 else "wide"))
     bytes_alg = synthetic.pframe_algorithmic_bytes(B, Hh, Ww)
 
@@ -351,14 +354,14 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "flow": args.flow, "warp_algo": args.algo,
                        "per_gpu": "each rank codes its own independent sequence (no data-path collective)",
                        "l2": "inputs larger than L2: 1.26 GB working set per frame vs 126 MB L2, no flush needed",
-                       "launch": ("CUDA graph replay of the frame's 25 hot-path launches, "
+                       "launch": (f"CUDA graph replay of the frame's {hp.n_launches} hot-path launches, "
                                   + ("serial order" if args.serial else
                                      "captured as their data-dependency DAG (one branch per launch: no "
                                      "op of the path consumes another's output; joined by bits_finalize)"
                                      if not args.branches4 else
                                      "captured as their data-dependency DAG (4 branches: feature warp | "
                                      "3-ch warps | mv entropy | res entropy, joined by bits_finalize)")),
-                       "bpp_check": bpp},
+                       "fuse_frame_warp": bool(args.fuse_frame_warp), "bpp_check": bpp},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": hp.n_launches * args.steps, "clocks": sampler.summary(),
         }

@@ -6,7 +6,8 @@ Host-side mirror of the reference's operator interface for this path
 Importing the package does not require a GPU; calling an op does (no CPU fallback).
 """
 from . import _lib, ans
-from .warp import torch_warp, warp_forward, warp_backward, set_flow_arithmetic, set_warp_algorithm
+from .warp import (torch_warp, warp_forward, warp_forward2, warp_backward, set_flow_arithmetic,
+                   set_warp_algorithm)
 from .entropy import (EntropyBottleneck, EntropyModel, GaussianConditional, LowerBound, ste_round,
                       bits_finalize, bpp_scale)
 from .fused import mc_blend, spynet_level_warp, warp_with_mse
@@ -14,7 +15,7 @@ from .patch import patch_reference, swap_entropy_models, unpatch_reference
 
 __version__ = "0.1.0"
 
-__all__ = ["torch_warp", "warp_forward", "warp_backward", "set_flow_arithmetic",
+__all__ = ["torch_warp", "warp_forward", "warp_forward2", "warp_backward", "set_flow_arithmetic",
            "set_warp_algorithm", "EntropyBottleneck", "EntropyModel", "GaussianConditional",
            "LowerBound", "ste_round", "bits_finalize", "bpp_scale", "patch_reference",
            "unpatch_reference", "swap_entropy_models", "spynet_level_warp", "warp_with_mse", "mc_blend"]

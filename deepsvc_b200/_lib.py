@@ -29,6 +29,8 @@ SIGNATURES = {
                                   c_float, c_float, c_float, c_float, c_int, c_int, c_int,
                                   _P, c_size_t, _P]),
     "dsvc_warp_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dsvc_warp_fwd2_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                   c_float, c_float, c_float, c_float, c_int, _P, c_size_t, _P]),
     "dsvc_warp_bwd_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                   c_float, c_float, c_float, c_float, c_int, c_int, _P]),
     "dsvc_warp_fused_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,

@@ -216,7 +216,8 @@ using namespace dsvc;
 int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* out,
                                  const float* lin_x, const float* lin_y, const WarpParams& p,
                                  bool force, void* workspace, size_t workspace_bytes,
-                                 cudaStream_t st);  // warp_persist.cu
+                                 cudaStream_t st, const float* input2 = nullptr, float* out2 = nullptr,
+                                 int C2 = 0);  // warp_persist.cu
 
 int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const float* flow, float* gin,
                                 float* gflow, const float* lin_x, const float* lin_y, const WarpParams& p,
@@ -310,6 +311,28 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
     else
         warp_fwd_nchw_gather<1><<<grid, block, 0, st>>>(input, flow, out, lin_x, lin_y, p, cpc, nchunk);
     DSVC_RETURN_LAST();
+}
+
+extern "C" int dsvc_warp_fwd2_f32(const float* input_a, const float* input_b, const float* flow,
+                                  float* out_a, float* out_b, int B, int Ca, int Cb, int H, int W,
+                                  const float* lin_x, const float* lin_y, float sx, float sy,
+                                  float inv_sx, float inv_sy, int flow_mode, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    DSVC_CHECK_ARG(warp_args_ok(input_a, flow, out_a, B, Ca, H, W, lin_x, lin_y));
+    DSVC_CHECK_ARG(input_b && out_b && Cb > 0);
+    DSVC_CHECK_ARG(flow_mode == 0 || flow_mode == 1);
+    WarpParams p{B, Ca + Cb, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+    if (Ca >= 8 && W >= 64 && H >= 32) {
+        const int r = dsvc_warp_fwd_persist_launch(input_a, flow, out_a, lin_x, lin_y, p, false, workspace,
+                                                   workspace_bytes, (cudaStream_t)stream, input_b, out_b, Cb);
+        if (r != -1) return r;
+    }
+    // shape not eligible for the shared launch: two ordinary launches (same results)
+    const int r = dsvc_warp_fwd_f32(input_a, flow, out_a, B, Ca, H, W, lin_x, lin_y, sx, sy, inv_sx, inv_sy,
+                                    flow_mode, DSVC_LAYOUT_NCHW, DSVC_WARP_AUTO, workspace, workspace_bytes, stream);
+    if (r) return r;
+    return dsvc_warp_fwd_f32(input_b, flow, out_b, B, Cb, H, W, lin_x, lin_y, sx, sy, inv_sx, inv_sy, flow_mode,
+                             DSVC_LAYOUT_NCHW, DSVC_WARP_AUTO, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {

@@ -164,8 +164,9 @@ __device__ __forceinline__ void scout_bbox(const float* __restrict__ fl, const f
 
 template <class Cfg>
 __global__ void __maxnreg__(Cfg::MAXREG)
-warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ in,
-                        const float* __restrict__ flow, float* __restrict__ out,
+warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2,
+                        const float* __restrict__ in, const float* __restrict__ in2,
+                        const float* __restrict__ flow, float* __restrict__ out, float* __restrict__ out2, int C1,
                         const float* __restrict__ lin_x, const float* __restrict__ lin_y,
                         WarpParams p, Schedule sch, WarpSched* __restrict__ sched) {
     constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, CC = Cfg::CC, STAGES = Cfg::STAGES;
@@ -330,8 +331,13 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
             long long tw_empty = 0;
             const int ngroups = (d.c_end - d.c_begin + CC - 1) / CC;
             const uint32_t tx_bytes = (uint32_t)d.nchunks * Cfg::CHUNK_FLOATS * sizeof(float);
-            const int plane0 = d.b * p.C + d.c_begin;
+            // channels [0, C1) live in the first tensor, [C1, p.C) in the second (same flow, same
+            // coordinates: e.g. the frame warp of video_model.py:37 riding on the feature warp)
             for (int g = 0; g < ngroups; ++g, ++it) {
+                const int cg = d.c_begin + g * CC;
+                const bool second = cg >= C1;
+                const CUtensorMap* tm = second ? &tmap2 : &tmap;
+                const int pl = second ? d.b * (p.C - C1) + (cg - C1) : d.b * C1 + cg;
                 const uint32_t s = it % STAGES;
 #ifdef DSVC_TRACE
                 const long long te0 = clock64();
@@ -343,7 +349,7 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
                 tma::mbar_arrive_expect_tx(full0 + 8u * s, tx_bytes);
                 const uint32_t dst = sbase0 + s * (uint32_t)(Cfg::STAGE_FLOATS * 4);
                 for (int k = 0; k < d.nchunks; ++k)
-                    tma::load_3d(dst + (uint32_t)k * (Cfg::CHUNK_FLOATS * 4), &tmap, d.bx0, plane0 + g * CC,
+                    tma::load_3d(dst + (uint32_t)k * (Cfg::CHUNK_FLOATS * 4), tm, d.bx0, pl,
                                  d.by0 + k * Cfg::ROWCHUNK, full0 + 8u * s);
             }
             DSVC_TR(du, 6, clock64());
@@ -392,7 +398,16 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
             for (int k = 0; k < PPT; ++k) {
                 if (!((vmask >> k) & 1u)) continue;
                 const int x = d.tx0 + (k % XH) * 32 + lane, y = d.ty0 + warp * RPW + k / XH;
-                gather_pixel<8>(in, flow, out, lin_x, lin_y, p, d.b, x, y, d.c_begin, d.c_end);
+                if (d.c_begin < C1) {
+                    WarpParams pa = p;
+                    pa.C = C1;
+                    gather_pixel<8>(in, flow, out, lin_x, lin_y, pa, d.b, x, y, d.c_begin, min(d.c_end, C1));
+                }
+                if (d.c_end > C1) {
+                    WarpParams pb = p;
+                    pb.C = p.C - C1;
+                    gather_pixel<8>(in2, flow, out2, lin_x, lin_y, pb, d.b, x, y, max(d.c_begin, C1) - C1, d.c_end - C1);
+                }
             }
             continue;
         }
@@ -402,8 +417,12 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
         //   (ry >> 3) * CHUNK_FLOATS + (ry & 7) * ROW_PITCH + c * BW + rx.
         const int ngroups = (d.c_end - d.c_begin + CC - 1) / CC;
         const int nch = d.c_end - d.c_begin;
-        float* obase = out + (size_t)(d.b * p.C + d.c_begin) * plane +
-                       (size_t)(d.ty0 + warp * RPW) * p.W + d.tx0 + lane;
+        const size_t toff = (size_t)(d.ty0 + warp * RPW) * p.W + d.tx0 + lane;
+        auto out_plane = [&](int c) -> float* {  // channel c of batch item d.b, at the thread's tile offset
+            return (c < C1 ? out + (size_t)(d.b * C1 + c) * plane
+                           : out2 + (size_t)(d.b * (p.C - C1) + (c - C1)) * plane) + toff;
+        };
+        float* obase = out_plane(d.c_begin);
         if (d.fast) {
             // interior tile, every east tap inside the image: byte addresses, immediate offsets
             float wnw[PPT], wne[PPT], wsw[PPT], wse[PPT];
@@ -440,6 +459,11 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
                 tw_full += clock64() - tf0;
 #endif
                 const uint32_t sbase = sbase0 + s * (uint32_t)(Cfg::STAGE_FLOATS * 4);
+                if (g > 0 && d.c_begin + g * CC == C1) {  // the unit crosses into the second tensor
+                    float* ob2 = out_plane(C1);
+#pragma unroll
+                    for (int r = 0; r < RPW; ++r) orow[r] = ob2 + (size_t)r * p.W;
+                }
                 uint32_t tn[PPT], ts[PPT];
 #pragma unroll
                 for (int k = 0; k < PPT; ++k) { tn[k] = a_n[k] + sbase; ts[k] = a_s[k] + sbase; }
@@ -508,7 +532,7 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const float* _
                     const int ch = g * CC + c;
                     if (ch < nch) {
                         const float* sc = sb + c * BW;
-                        float* oc = obase + (size_t)ch * plane;
+                        float* oc = out_plane(d.c_begin + ch);
 #pragma unroll
                         for (int r = 0; r < RPW; ++r)
 #pragma unroll
@@ -539,14 +563,18 @@ using namespace dsvc;
 template <class Cfg>
 static int launch_persist(const float* input, const float* flow, float* out, const float* lin_x,
                           const float* lin_y, const WarpParams& p, void* workspace,
-                          size_t workspace_bytes, cudaStream_t st) {
+                          size_t workspace_bytes, cudaStream_t st, const float* input2 = nullptr,
+                          float* out2 = nullptr, int C2 = 0) {
+    // p.C counts the channels of both tensors; the first one has C1 = p.C - C2 of them
+    const int C1 = p.C - C2;
+    if (C2 > 0 && (C1 % Cfg::CC != 0 || !input2 || !out2)) return -1;
     auto encode = tensor_map_encoder();
     if (!encode) return -1;
     if (!workspace || workspace_bytes < sizeof(WarpSched) || !aligned16(workspace))
         return -1;  // no scheduler state: the caller uses the gather kernel
     CUtensorMap tm;
     // tensor viewed as (x, plane, y): the box lands in shared memory as [8 rows][CC][BW]
-    const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)p.B * p.C, (cuuint64_t)p.H};
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.W, (cuuint64_t)p.B * C1, (cuuint64_t)p.H};
     const cuuint64_t gstride[2] = {(cuuint64_t)p.H * p.W * 4, (cuuint64_t)p.W * 4};
     const cuuint32_t box[3] = {(cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::CC, (cuuint32_t)Cfg::ROWCHUNK};
     const cuuint32_t estr[3] = {1, 1, 1};
@@ -555,6 +583,14 @@ static int launch_persist(const float* input, const float* flow, float* out, con
                               gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return -1;
+    CUtensorMap tm2 = tm;
+    if (C2 > 0) {
+        const cuuint64_t gdim2[3] = {(cuuint64_t)p.W, (cuuint64_t)p.B * C2, (cuuint64_t)p.H};
+        if (encode(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(input2), gdim2, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -1;
+    }
     // per-device set-up (function attributes and SM counts belong to the device, not the process)
     static unsigned long long attr_set = 0;
     static int sms_of[64];
@@ -606,7 +642,7 @@ static int launch_persist(const float* input, const float* flow, float* out, con
     }
 #endif
     warp_fwd_persist_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
-        tm, input, flow, out, lin_x, lin_y, p, sch, static_cast<WarpSched*>(workspace));
+        tm, tm2, input, input2, flow, out, out2, C1, lin_x, lin_y, p, sch, static_cast<WarpSched*>(workspace));
 #ifdef DSVC_TRACE
     if (trace) {
         cudaStreamSynchronize(st);
@@ -630,9 +666,12 @@ static int launch_persist(const float* input, const float* flow, float* out, con
 int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* out,
                                  const float* lin_x, const float* lin_y, const WarpParams& p,
                                  bool force, void* workspace, size_t workspace_bytes,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const float* input2, float* out2, int C2) {
     // TMA needs 16-byte aligned rows and base; small / few-channel warps gain nothing
-    if (p.W % 4 != 0 || !aligned16(input)) return -1;
+    if (p.W % 4 != 0 || !aligned16(input) || (C2 > 0 && !aligned16(input2))) return -1;
+    if (C2 > 0)  // two tensors, one flow: the default configuration only
+        return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6, 2, 72>>(input, flow, out, lin_x, lin_y, p, workspace,
+                                                                      workspace_bytes, st, input2, out2, C2);
     if (!force && (p.C < 8 || p.W < 64 || p.H < 32)) return -1;
     if ((long long)p.B * p.C > (1ll << 30)) return -1;
     static int cfg = -1;

@@ -25,7 +25,7 @@ NUM_SLICES = 8
 
 class PFrameHotPath:
     def __init__(self, inputs: dict, models: dict, flow_mode=_lib.FLOW_MUL_RECIPROCAL,
-                 warp_algo=_lib.WARP_AUTO):
+                 warp_algo=_lib.WARP_AUTO, fuse_frame_warp=False):
         """inputs: tensors from ``synthetic.make_pframe_inputs`` already on one CUDA
         device; models: {"mv": (EntropyBottleneck, GaussianConditional), "res": (...)}
         (this package's drop-in classes, on the same device, eval mode)."""
@@ -47,8 +47,14 @@ class PFrameHotPath:
         self.out["spynet"] = []
         for img, fl in zip(inputs["pyr_img"], inputs["pyr_flow"]):
             self.out["spynet"].append(self._bind_warp(img, fl))
-        self.out["warped_frame"] = self._bind_warp(inputs["ref_frame"], inputs["flow"])
-        self.out["warped_feature"] = self._bind_warp(inputs["feature"], inputs["flow"])
+        if fuse_frame_warp:
+            # the frame warp (video_model.py:37) and the feature warp (modules.py:429) use the same
+            # flow: one launch (dsvc_warp_fwd2_f32), 24 launches per frame, bit-identical outputs
+            self.out["warped_feature"], self.out["warped_frame"] = self._bind_warp2(
+                inputs["feature"], inputs["ref_frame"], inputs["flow"])
+        else:
+            self.out["warped_frame"] = self._bind_warp(inputs["ref_frame"], inputs["flow"])
+            self.out["warped_feature"] = self._bind_warp(inputs["feature"], inputs["flow"])
 
         # ---- entropy: partial-sum buffer with one segment per codec
         seg = [0]
@@ -121,6 +127,20 @@ class PFrameHotPath:
             lin_y.data_ptr(), sx, sy, inv_sx, inv_sy, self.flow_mode, _lib.LAYOUT_NCHW,
             self.warp_algo, _lib.ptr(ws), 0 if ws is None else ws.numel()), f"warp_c{C}_{H}x{W}"))
         return out
+
+    def _bind_warp2(self, inp_a, inp_b, flow):
+        B, Ca, H, W = inp_a.shape
+        Cb = inp_b.shape[1]
+        out_a, out_b = torch.empty_like(inp_a), torch.empty_like(inp_b)
+        lin_x, lin_y = _base_grids(inp_a.device, H, W)
+        sx, sy, inv_sx, inv_sy = _scales(H, W)
+        ws = warp_workspace(inp_a.device, B, H, W, private=True)
+        self._keep += [out_a, out_b, lin_x, lin_y, ws]
+        self._calls.append((self.lib.dsvc_warp_fwd2_f32, (
+            inp_a.data_ptr(), inp_b.data_ptr(), flow.data_ptr(), out_a.data_ptr(), out_b.data_ptr(),
+            B, Ca, Cb, H, W, lin_x.data_ptr(), lin_y.data_ptr(), sx, sy, inv_sx, inv_sy, self.flow_mode,
+            _lib.ptr(ws), ws.numel()), f"warp_c{Ca}_{H}x{W}+c{Cb}"))
+        return out_a, out_b
 
     def run(self):
         """Enqueue the frame's launches on the current stream."""

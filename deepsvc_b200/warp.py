@@ -126,6 +126,34 @@ def warp_forward(inp, flow, flow_mode=None, algo=None):
     return out
 
 
+def warp_forward2(inp_a, inp_b, flow, flow_mode=None):
+    """(torch_warp(inp_a, flow), torch_warp(inp_b, flow)) in one launch (no autograd): two tensors
+    that share a flow -- ``video_model.py:37`` and ``modules.py:429`` both warp by ``recon_mv``.
+    Bit-identical to two ``warp_forward`` calls."""
+    _check(inp_a, flow)
+    _check(inp_b, flow)
+    if not (inp_a.is_contiguous() and inp_b.is_contiguous()):
+        raise RuntimeError("deepsvc_b200.warp_forward2: contiguous NCHW inputs required")
+    if (inp_a.requires_grad or inp_b.requires_grad or flow.requires_grad) and torch.is_grad_enabled():
+        raise RuntimeError("deepsvc_b200.warp_forward2: inference-only (use torch_warp for training)")
+    B, Ca, H, W = inp_a.shape
+    Cb = inp_b.shape[1]
+    out_a, out_b = torch.empty_like(inp_a), torch.empty_like(inp_b)
+    if out_a.numel() == 0 or out_b.numel() == 0:
+        return warp_forward(inp_a, flow, flow_mode), warp_forward(inp_b, flow, flow_mode)
+    lin_x, lin_y = _base_grids(inp_a.device, H, W)
+    sx, sy, inv_sx, inv_sy = _scales(H, W)
+    ws = warp_workspace(inp_a.device, B, H, W)
+    with torch.cuda.device(inp_a.device):
+        err = _lib.load().dsvc_warp_fwd2_f32(
+            inp_a.data_ptr(), inp_b.data_ptr(), flow.data_ptr(), out_a.data_ptr(), out_b.data_ptr(),
+            B, Ca, Cb, H, W, lin_x.data_ptr(), lin_y.data_ptr(), sx, sy, inv_sx, inv_sy,
+            _flow_mode if flow_mode is None else flow_mode, _lib.ptr(ws), ws.numel(),
+            _lib.stream_ptr(inp_a.device))
+    _lib.check(err, "dsvc_warp_fwd2_f32")
+    return out_a, out_b
+
+
 def warp_backward(grad_out, inp, flow, need_input_grad=True, need_flow_grad=True, flow_mode=None):
     """Raw backward launch: returns (grad_input | None, grad_flow | None)."""
     _check(inp, flow)

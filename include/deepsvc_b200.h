@@ -82,6 +82,19 @@ int dsvc_warp_fwd_f32(const float* input, const float* flow, float* out,
                       void* workspace, size_t workspace_bytes, void* stream);
 size_t dsvc_warp_workspace_bytes(int B, int H, int W);
 
+/* Two tensors warped by ONE flow in one launch: out_a = torch_warp(input_a, flow),
+ * out_b = torch_warp(input_b, flow), bit-identical to two dsvc_warp_fwd_f32 calls.
+ * In DeepSVC.forward the frame warp of video_model.py:37 and the feature warp of
+ * modules.py:429 share recon_mv: the frame's 3 planes ride on the persistent staged kernel of
+ * the 64-ch feature warp (same source coordinates and staging boxes, a second tensor map)
+ * instead of paying a second few-channel launch.  NCHW fp32, both [B,C*,H,W]; shapes the
+ * staged kernel cannot take (Ca < 8, W % 4 != 0, small images) run as two ordinary launches. */
+int dsvc_warp_fwd2_f32(const float* input_a, const float* input_b, const float* flow,
+                       float* out_a, float* out_b, int B, int Ca, int Cb, int H, int W,
+                       const float* lin_x, const float* lin_y,
+                       float sx, float sy, float inv_sx, float inv_sy, int flow_mode,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* Gradient of the above (autograd of modules.py:25-62 = ATen
  * grid_sampler_2d_backward + the division by sx/sy).
  * grad_input [B,C,H,W] (nullable) MUST be zero-filled by the caller: taps are

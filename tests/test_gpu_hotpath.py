@@ -58,6 +58,30 @@ def test_pframe_vs_oracle_and_graph(oracle, B, H, W):
     assert (got2["bpp_mv"], got2["bpp_res"]) == first
 
 
+def test_pframe_fused_frame_warp_variant(oracle):
+    """PFrameHotPath(fuse_frame_warp=True): 24 launches, outputs bit-identical to the 25-launch
+    drop-in sequence (eager and graph replay)."""
+    import deepsvc_b200 as dsvc
+    from deepsvc_b200 import synthetic
+    from deepsvc_b200.hotpath import PFrameHotPath
+    dev = torch.device("cuda:0")
+    cpu_in = synthetic.make_pframe_inputs(B=1, H=256, W=448, seed=16)
+    mg = {name: (dsvc.EntropyBottleneck(ch).to(dev).eval(), dsvc.GaussianConditional(None).to(dev).eval())
+          for name, ch in (("mv", 64), ("res", 96))}
+    gin = synthetic.to_device(cpu_in, dev)
+    ref = PFrameHotPath(gin, mg)
+    ref.run()
+    hp = PFrameHotPath(gin, mg, fuse_frame_warp=True)
+    assert hp.n_launches == 24 and ref.n_launches == 25
+    hp.capture()
+    hp.replay()
+    torch.cuda.synchronize()
+    r, h = ref.results(), hp.results()
+    assert torch.equal(r["warped_frame"], h["warped_frame"])
+    assert torch.equal(r["warped_feature"], h["warped_feature"])
+    assert (r["bpp_mv"], r["bpp_res"]) == (h["bpp_mv"], h["bpp_res"])
+
+
 def test_dropin_on_reference_shaped_codec(oracle):
     """A codec with the reference's call pattern (image_model.py:151-199: EB on z, 8 slice
     GC calls fed by convs, ste_round y_hat) gives the same y_hat (bit-exact) and bpp

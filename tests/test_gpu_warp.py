@@ -409,3 +409,27 @@ def test_full_size_4k_forward_and_backward_properties(oracle):
     gi, gf = warp_backward(go, x16.detach(), flow, True, True)
     assert (gi - gi_ref).abs().max().item() <= 1e-4 * max(1.0, gi_ref.abs().max().item())
     assert (gf - gf_ref).abs().max().item() <= 1e-4 * max(1.0, gf_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["smooth", "stress", "border"])
+@pytest.mark.parametrize("shape", [(1, 64, 3, 128, 192), (2, 16, 3, 100, 132), (1, 8, 5, 64, 64), (1, 9, 2, 33, 100),
+                                   (1, 3, 3, 40, 64), (1, 64, 3, 1088, 1920)])
+def test_two_tensors_one_flow_bit_identical(shape, kind):
+    """dsvc_warp_fwd2_f32 (frame planes riding on the feature warp's staged launch, or two plain
+    launches for shapes the staged kernel does not take) == two separate torch_warp calls, bit for bit;
+    the scheduler state is left zeroed."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import synthetic
+    from deepsvc_b200.warp import warp_forward, warp_forward2, warp_workspace
+    B, Ca, Cb, H, W = shape
+    g = torch.Generator().manual_seed(Ca * 7 + H + W)
+    a = torch.randn(B, Ca, H, W, generator=g).to(_dev())
+    b = torch.rand(B, Cb, H, W, generator=g).to(_dev())
+    flow = synthetic.make_flow(kind, B, H, W, g).to(_dev())
+    for _ in range(2):
+        oa, ob = warp_forward2(a, b, flow)
+        assert torch.equal(oa, warp_forward(a, flow))
+        assert torch.equal(ob, warp_forward(b, flow))
+    assert int(warp_workspace(_dev(), B, H, W).abs().sum().item()) == 0
+    with pytest.raises(RuntimeError):
+        warp_forward2(a.requires_grad_(True), b, flow)
