@@ -164,3 +164,48 @@ def allreduce_gradients(params, bucket_bytes: int = 32 << 20, clamp: float = Non
             p.grad.copy_(flat[off:off + n].view_as(p.grad))
             off += n
     return len(buckets)
+
+
+class FlatGradBuckets:
+    """The same reduction without the per-step gather/scatter copies: gradients LIVE in flat fp32
+    buckets (every ``p.grad`` is a view into one), so a step's sync is one in-place NCCL all-reduce
+    per bucket plus two elementwise passes (mean, clamp).  Create it once after the model is on
+    its device; backward passes then accumulate straight into the buckets."""
+
+    def __init__(self, params, bucket_bytes: int = 32 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets = []
+        cur, size = [], 0
+        for p in self.params:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(self._make(cur))
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(self._make(cur))
+
+    @staticmethod
+    def _make(ps):
+        flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            view = flat[off:off + n].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            off += n
+        return flat
+
+    def allreduce(self, clamp: float = None) -> int:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        works = [dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
+                 for f in self.buckets]
+        for f, w in zip(self.buckets, works):
+            if w is not None:
+                w.wait()
+                f.div_(world)
+            if clamp is not None:  # after the reduction (Learner.py:1687-1691 on the reduced gradient)
+                f.clamp_(-clamp, clamp)
+        return len(self.buckets)

@@ -79,8 +79,15 @@ params = [torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(3, 
 for p in params:
     p.grad = torch.full_like(p, float(rank + 1) * 2.0)
 nb = shard.allreduce_gradients(params, bucket_bytes=16, clamp=1.0)
+params2 = [torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(3, 2))]
+for p in params2:
+    p.grad = torch.full_like(p, float(rank + 1) * 0.25)
+fb = shard.FlatGradBuckets(params2, bucket_bytes=16)
+nb2 = fb.allreduce(clamp=1.0)
+params2[1].grad.add_(1.0)                      # grads are views of the buckets
 out = {"rank": rank, "frames": frames, "tmax": tmax, "total": total, "all": allm,
-       "g0": params[0].grad.tolist(), "buckets": nb}
+       "g0": params[0].grad.tolist(), "buckets": nb,
+       "f0": params2[0].grad.tolist(), "f1_in_bucket": fb.buckets[1].tolist(), "fbuckets": nb2}
 if rank == 0:
     print("RESULT " + json.dumps(out), flush=True)
 dist.barrier()
@@ -107,3 +114,5 @@ def test_world_size_2_gloo(tmp_path):
     assert [m["frames"] for m in out["all"]] == [11 * 31, 10 * 31]
     assert out["g0"] == [1.0] * 5                              # mean(2,4)=3 -> clamped to 1
     assert out["buckets"] == 2
+    assert out["f0"] == [0.375] * 5 and out["fbuckets"] == 2     # mean(0.25, 0.5), in place
+    assert out["f1_in_bucket"] == [1.375] * 6                     # p.grad is a view of its bucket
