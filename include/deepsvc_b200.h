@@ -97,8 +97,9 @@ int dsvc_warp_fwd2_f32(const float* input_a, const float* input_b, const float* 
 
 /* Gradient of the above (autograd of modules.py:25-62 = ATen
  * grid_sampler_2d_backward + the division by sx/sy).
- * grad_input [B,C,H,W] (nullable) MUST be zero-filled by the caller: taps are
- * accumulated with atomics.  grad_flow [B,2,H,W] (nullable) is overwritten. */
+ * grad_input [B,C,H,W] (nullable) MUST be zero-filled by the caller: contributions are
+ * added with global reductions (per tile after combining in shared memory, or per tap).
+ * grad_flow [B,2,H,W] (nullable) is overwritten.  Kernel choice: dsvc_set_warp_bwd_algo. */
 int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* flow,
                       float* grad_input, float* grad_flow,
                       int B, int C, int H, int W,
@@ -129,7 +130,8 @@ int dsvc_blend_f32(const float* weight, const float* warped, const float* pred, 
 
 /* Kernel choice of dsvc_warp_bwd_f32 (process-wide; tests and profiling).
  * DSVC_WARP_BWD_AUTO (0, default, or $DSVC_BWD_ALGO): the shared-memory staged kernel
- * (per-tile transposed-warp CSR + TMA tensor reduce-add into grad_input, csrc/warp_bwd_staged.cu)
+ * (per-tile transposed-warp CSR, run sums in a shared-memory out-box, row-contiguous RED.ADD.v4.F32
+ * into grad_input; csrc/warp_bwd_staged.cu)
  * when C >= 8, W % 4 == 0, W >= 64, H >= 16 and the pointers are 16-byte aligned, else the
  * per-pixel RED.ADD kernel; DSVC_WARP_BWD_DIRECT (1): always the per-pixel kernel;
  * DSVC_WARP_BWD_STAGED (2): the staged kernel or cudaErrorInvalidValue. */
