@@ -36,10 +36,31 @@ if ROOT not in sys.path:
 METRIC = "1080p P-frames/sec (warp+entropy path)"
 UNIT = "frames/s"
 H, W, B = 1088, 1920, 1
-WORKLOAD = ("cfg2: 1920x1088 (padded 1080p) P-frame, B=1, DeepSVC.forward hot path = 4 SpyNet "
-            "3-ch warps + 3-ch frame warp + 64-ch feature warp + 16 GaussianConditional slices "
-            "(8x8ch mv, 8x12ch res @68x120) + 2 EntropyBottleneck (64/96ch @17x30) + bit sums; "
-            "smooth SpyNet-like flow")
+MIN_TIMED_S = 0.5   # the K-step block is repeated until the timed region is at least this long
+# frame sizes BASELINE.json's configs name (padded to multiples of 64, modules.py:76-89)
+SIZES = {"cfg1": (256, 448), "cfg2": (1088, 1920), "cfg5": (2176, 3840)}
+
+
+def labels(Hh, Ww, flow="smooth"):
+    """(metric, workload, size tag) for a frame size: the line is labelled from the size it ran
+    at, never from a constant.  Sizes outside BASELINE.json's configs are refused."""
+    tag = {v: k for k, v in SIZES.items()}.get((Hh, Ww))
+    if tag is None:
+        raise SystemExit(f"bench.py: {Ww}x{Hh} is not a BASELINE.json frame size "
+                         f"(use one of {sorted(SIZES.values())})")
+    name = {"cfg1": "448x256 (Vimeo90k-shaped)", "cfg2": "1920x1088 (padded 1080p)",
+            "cfg5": "3840x2176 (padded 2160p)"}[tag]
+    metric = {"cfg1": "448x256 P-frames/sec (warp+entropy path)", "cfg2": METRIC,
+              "cfg5": "2160p P-frames/sec (warp+entropy path)"}[tag]
+    h16, w16, h64, w64 = Hh // 16, Ww // 16, Hh // 64, Ww // 64
+    workload = (f"{tag}: {name} P-frame, B=1, DeepSVC.forward hot path = 4 SpyNet "
+                "3-ch warps + 3-ch frame warp + 64-ch feature warp + 16 GaussianConditional slices "
+                f"(8x8ch mv, 8x12ch res @{h16}x{w16}) + 2 EntropyBottleneck (64/96ch @{h64}x{w64}) + bit sums; "
+                f"{flow} flow" + (" (SpyNet-like)" if flow == "smooth" else ""))
+    return metric, workload, tag
+
+
+WORKLOAD = labels(H, W)[1]
 
 
 def parse():
@@ -61,9 +82,16 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 40)")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "codec"],
-                    help="cfg2 (default, the headline line): 1080p P-frame forward path; cfg3: training "
-                         "frame-step (B=8, 256x256, forward + backward), a secondary line")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5", "codec", "dropin"],
+                    help="cfg2 (default, the headline line): 1080p P-frame forward path; cfg1 / cfg5: the same "
+                         "path at 448x256 (rotated input sets, see config.l2) / 3840x2176; cfg3: training "
+                         "frame-step (B=8, 256x256, forward + backward); cfg4: GOP sharding; codec: symbol "
+                         "pipeline + range coder; dropin: the unmodified reference DeepSVC.forward stock vs "
+                         "patched (needs oracle/_ref) -- all secondary lines")
+    ap.add_argument("--train", action="store_true", help="--workload dropin: time a training step instead of inference")
+    ap.add_argument("--sets", type=int, default=0,
+                    help="distinct input sets rotated between steps (default: 1, or 8 at cfg1 whose 69 MB "
+                         "working set would otherwise sit in the 126 MB L2)")
     ap.add_argument("--gop", type=int, default=32, help="cfg4: GOP size (32 = BASELINE, 12 = test_video.py:22)")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
@@ -203,8 +231,16 @@ def time_cpu_path(cpu_inputs, models_o, steps, warmup, threads, budget_s):
         dt = time.perf_counter() - t0
     fps = steps * frac / dt
     desc = (f"{steps} steps (+{warmup} warm-up) of the top {rows}/{Hh} rows of every tensor of one "
-            f"1080p P-frame (value scaled by {frac:.4f}), torch {threads} threads, {dt:.1f}s")
+            f"{cpu_inputs['ref_frame'].shape[3]}x{Hh} P-frame (value scaled by {frac:.4f}), torch {threads} threads, {dt:.1f}s")
     return fps, desc, dt / steps
+
+
+def frame_size(args):
+    if args.workload in SIZES:
+        if (args.height, args.width) != (H, W) and (args.height, args.width) != SIZES[args.workload]:
+            raise SystemExit("bench.py: --height/--width contradict --workload")
+        return SIZES[args.workload] if args.workload != "cfg2" else (args.height, args.width)
+    return args.height, args.width
 
 
 def run_reference(args):
@@ -214,16 +250,18 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    cpu_in = synthetic.make_pframe_inputs(B=B, H=args.height, W=args.width, seed=16, flow_kind=args.flow)
+    Hh, Ww = frame_size(args)
+    metric, workload, _ = labels(Hh, Ww, args.flow)
+    cpu_in = synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16, flow_kind=args.flow)
     models = build_models("cpu")
     models_o = oracle_models(models)
     fps, desc, s_per_step = time_cpu_path(cpu_in, models_o, args.steps, max(args.warmup, 1) if args.steps > 3 else 1,
                                           threads, budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "flow": args.flow},
+        "data": "synthetic", "config": {"workload": workload, "flow": args.flow},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -233,11 +271,49 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def timed_blocks(replay, steps, barrier, dev, min_s=MIN_TIMED_S, max_blocks=400):
+    """Times blocks of exactly `steps` calls of `replay(i)` with CUDA events on the current
+    stream until the timed region is at least `min_s` long; returns (median block ms, per-block
+    ms list).  Bracketed by barrier + synchronize on both sides."""
+    import torch
+    barrier()
+    blocks, total, i = [], 0.0, 0
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            replay(i)
+            i += 1
+        e1.record()
+        e1.synchronize()
+        blocks.append(e0.elapsed_time(e1))
+        total += blocks[-1]
+        if total >= min_s * 1e3 or len(blocks) >= max_blocks:
+            break
+    barrier()
+    return statistics.median(blocks), blocks
+
+
+def time_gpu_eager(fn, dev, steps=10, warmup=3):
+    """ms per call of an eager GPU function (CUDA events around `steps` calls)."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / steps
+
+
 def run_ours(args):
     import torch
     import deepsvc_b200  # noqa: F401
     from deepsvc_b200 import _lib, shard, synthetic
-    from deepsvc_b200.hotpath import HostSession, PFrameHotPath
+    from deepsvc_b200.hotpath import HostSession, PFrameHotPath, pframe_eager
 
     rank, local_rank, world = shard.init_distributed()
     if not torch.cuda.is_available():
@@ -246,37 +322,50 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     numa_bound = shard.bind_to_gpu_numa_node(local_rank) if world > 1 else False
-    Hh, Ww = args.height, args.width
+    Hh, Ww = frame_size(args)
+    metric, workload, tag = labels(Hh, Ww, args.flow)
     algo = {"auto": _lib.WARP_AUTO, "gather": _lib.WARP_GATHER, "tma": _lib.WARP_TMA}[args.algo]
-
-    cpu_in = synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16 + rank, flow_kind=args.flow)
-    models = build_models(dev)
-    gpu_in = synthetic.to_device(cpu_in, dev)
-    hp = PFrameHotPath(gpu_in, models, warp_algo=algo, fuse_frame_warp=args.fuse_frame_warp)
-    hp.capture(dag=False if args.serial else (True if args.branches4 else "wide"))
     bytes_alg = synthetic.pframe_algorithmic_bytes(B, Hh, Ww)
+    # L2: 126 MB.  A frame whose working set fits is run over `nsets` distinct input/output sets
+    # in rotation so that every replay finds its data in HBM, not in L2
+    nsets = args.sets or (8 if bytes_alg["total"] < (256 << 20) else 1)
+
+    models = build_models(dev)
+    cpu_sets = [synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16 + rank + 100 * i, flow_kind=args.flow)
+                for i in range(nsets)]
+    cpu_in = cpu_sets[0]
+    hps = []
+    for ci in cpu_sets:
+        hp = PFrameHotPath(synthetic.to_device(ci, dev), models, warp_algo=algo, fuse_frame_warp=args.fuse_frame_warp)
+        hp.capture(dag=False)                                   # "serial": DeepSVC.forward's own order
+        hp.capture(dag=True if args.branches4 else "wide")      # data-dependency DAG
+        hps.append(hp)
+    hp, gpu_in = hps[0], hps[0].inputs
+    main_mode = "serial" if args.serial else ("branches4" if args.branches4 else "wide")
 
     def barrier():
         if world > 1:
             torch.distributed.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
 
-    # ---- main timed region: K graph replays, inputs resident in HBM
-    for _ in range(max(args.warmup, 3)):
-        hp.replay()
-    barrier()
+    # ---- main timed region: blocks of K graph replays, inputs resident in HBM
+    for i in range(max(args.warmup, 3)):
+        hps[i % nsets].replay(main_mode)
     sampler = ClockSampler(local_rank)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler:
-        ev0.record()
-        for _ in range(args.steps):
-            hp.replay()
-        ev1.record()
-        barrier()
-    ms_local = ev0.elapsed_time(ev1)
+        ms_local, blocks = timed_blocks(lambda i: hps[i % nsets].replay(main_mode), args.steps, barrier, dev)
     ms = shard.max_over_ranks(ms_local, dev)
     value = world * args.steps / (ms * 1e-3)
     bpp = hp.results()["bpp"]
+    # the same frame in the serial order of DeepSVC.forward (what a caller that interleaves the
+    # conv transforms can issue); reported next to the DAG number
+    other = "serial" if main_mode != "serial" else "wide"
+    for i in range(3):
+        hps[i % nsets].replay(other)
+    with sampler:
+        ms_other, _ = timed_blocks(lambda i: hps[i % nsets].replay(other), args.steps, barrier, dev)
+    ms_other = shard.max_over_ranks(ms_other, dev)
+    order_ms = {main_mode: ms / args.steps, other: ms_other / args.steps}
 
     # ---- dominant kernel (64-ch feature warp) timed live with CUDA events, same stream,
     #      inside K eager steps of the whole frame (so caches/clocks see the full step)
@@ -285,7 +374,7 @@ def run_ours(args):
     n_k = min(args.steps, 200)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
     for i in range(n_k):
-        for j, (fn, a, name) in enumerate(hp._calls):
+        for j, (fn, a, name) in enumerate(hps[i % nsets]._calls):
             if j == feat_idx:
                 evs[i][0].record(st)
             err = fn(*a, st.cuda_stream)
@@ -297,13 +386,16 @@ def run_ours(args):
     k_ms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in evs[1:] or evs)
     peak, peak_src = measured_peak()
     achieved = bytes_alg["feature"] / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "warp_fwd (64-ch feature warp, 1088x1920)",
+    frame_gbs = bytes_alg["total"] / (ms_local / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"warp_fwd_persist (64-ch feature warp, {Hh}x{Ww})",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_launch": bytes_alg["feature"], "kernel_ms": k_ms,
-                "whole_frame": {"algorithmic_bytes": bytes_alg["total"],
-                                "achieved_gbs": bytes_alg["total"] * args.steps / (ms_local * 1e-3) / 1e9,
-                                "frac_of_peak": bytes_alg["total"] * args.steps / (ms_local * 1e-3) / 1e9 / peak}}
+                "frac_of_nominal_8tbs": achieved / 8000.0,
+                "whole_frame": {"algorithmic_bytes": bytes_alg["total"], "achieved_gbs": frame_gbs,
+                                "frac_of_peak": frame_gbs / peak, "frac_of_nominal_8tbs": frame_gbs / 8000.0,
+                                "serial_order_frac_of_peak":
+                                    bytes_alg["total"] / (order_ms["serial"] * 1e-3) / 1e9 / peak}}
     # DRAM bytes of the same kernel from the committed ncu --set full capture (per launch)
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(prof) and (Hh, Ww, B) == (1088, 1920, 1):
@@ -324,46 +416,81 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with sampler:
+            n_done = 0
             e0.record()
-            for _ in range(n_e):
+            t0 = time.perf_counter()
+            while n_done < n_e or (time.perf_counter() - t0 < MIN_TIMED_S and n_done < 100 * n_e):
                 sess.process()
+                n_done += 1
             sess.drain()
             e1.record()
             barrier()
         e_ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
-        e2e = {"value": world * n_e / (e_ms * 1e-3), "unit": UNIT,
+        n_done = int(shard.sum_over_ranks(n_done, dev))
+        e2e = {"value": n_done / (e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": sess.h2d_bytes, "d2h_bytes_per_step": sess.d2h_bytes,
-               "steps": n_e, "ms_per_step": e_ms / n_e,
+               "steps": n_done // world, "ms_per_step": e_ms / (n_done / world),
                "api": "deepsvc_b200.hotpath.HostSession.process (pinned host tensors in / out)",
                "cpu_affinity": "GPU-local NUMA node (NVML)" if numa_bound else "inherited"}
         del sess
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on this box's host cores
-    cpu_baseline = None
+    # ---- baselines beside it (rank 0, N=1 only)
+    cpu_baseline = cpu_1t = stock_gpu = dropin_eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import reference_ops as R   # the checker, timed as the reported baselines
+        models_o = oracle_models(models)
+        # (a) the oracle's ops moved .cuda(): the reference's own CUDA branch (modules.py:44-62
+        #     F.grid_sample + eager compressai-equivalent chain), eager, the way the reference runs
+        models_og = {k: (eb.to(dev), gc.to(dev)) for k, (eb, gc) in oracle_models(models).items()}
+        with torch.no_grad():
+            sg_ms = time_gpu_eager(lambda: R.pframe_hotpath(gpu_in, models_og), dev, steps=10, warmup=3)
+            # (b) the same calls through this package's public drop-in API, eager, no graph
+            de_ms = time_gpu_eager(lambda: pframe_eager(gpu_in, models), dev, steps=20, warmup=3)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                pframe_eager(gpu_in, models)
+            de_host_ms = (time.perf_counter() - t0) / 20 * 1e3    # host time to ISSUE a frame (no sync)
+            torch.cuda.synchronize(dev)
+        stock_gpu = {"value": 1e3 / sg_ms, "unit": UNIT, "ms_per_step": sg_ms, "steps": 10,
+                     "kind": "oracle ops on cuda:0 = the reference's CUDA branch (modules.py:44-62 grid_sample "
+                             "+ eager compressai-equivalent entropy chain + torch log/sum), eager, CUDA events"}
+        dropin_eager = {"value": 1e3 / de_ms, "unit": UNIT, "ms_per_step": de_ms, "host_issue_ms_per_step": de_host_ms,
+                        "steps": 20, "vs_stock_gpu": sg_ms / de_ms,
+                        "kind": "deepsvc_b200.hotpath.pframe_eager: the drop-in ops called eagerly in "
+                                "DeepSVC.forward's order (no pre-bound launches, no CUDA graph)"}
         threads = os.cpu_count() or 1
-        fps, desc, _ = time_cpu_path(cpu_in, oracle_models(models), steps=3, warmup=1,
-                                     threads=threads, budget_s=25.0)
+        fps, desc, _ = time_cpu_path(cpu_in, models_o, steps=3, warmup=1, threads=threads, budget_s=20.0)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc}
+        # the reference's own evaluation setting: torch.set_num_threads(1) (test_video.py:16)
+        fps1, desc1, _ = time_cpu_path(cpu_in, models_o, steps=2, warmup=1, threads=1, budget_s=12.0)
+        cpu_1t = {"value": fps1, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc1}
+        torch.set_num_threads(threads)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "flow": args.flow, "warp_algo": args.algo,
+            "config": {"workload": workload, "flow": args.flow, "warp_algo": args.algo,
                        "per_gpu": "each rank codes its own independent sequence (no data-path collective)",
-                       "l2": "inputs larger than L2: 1.26 GB working set per frame vs 126 MB L2, no flush needed",
+                       "l2": (f"inputs larger than L2: {bytes_alg['total'] / 1e6:.0f} MB working set per frame vs 126 MB L2, no flush needed"
+                              if nsets == 1 else
+                              f"{nsets} distinct input/output sets replayed in rotation ({nsets} x {bytes_alg['total'] / 1e6:.0f} MB "
+                              "> 126 MB L2): every replay reads its frame from HBM"),
+                       "timed_region": f"{len(blocks)} blocks of {args.steps} steps (>= {MIN_TIMED_S} s in total); "
+                                       "value = steps / median block time, max over ranks",
                        "launch": (f"CUDA graph replay of the frame's {hp.n_launches} hot-path launches, "
-                                  + ("serial order" if args.serial else
-                                     "captured as their data-dependency DAG (one branch per launch: no "
-                                     "op of the path consumes another's output; joined by bits_finalize)"
-                                     if not args.branches4 else
-                                     "captured as their data-dependency DAG (4 branches: feature warp | "
-                                     "3-ch warps | mv entropy | res entropy, joined by bits_finalize)")),
+                                  + {"serial": "serial order of DeepSVC.forward",
+                                     "wide": "captured as their data-dependency DAG (one branch per launch: no "
+                                             "op of the path consumes another's output; joined by bits_finalize)",
+                                     "branches4": "captured as their data-dependency DAG (4 branches: feature warp | "
+                                                  "3-ch warps | mv entropy | res entropy, joined by bits_finalize)"}[main_mode]),
+                       "serial_ms_per_step": order_ms["serial"], "serial_value": world * 1e3 / order_ms["serial"],
+                       "dag_ms_per_step": order_ms.get("wide", order_ms.get("branches4")),
                        "fuse_frame_warp": bool(args.fuse_frame_warp), "bpp_check": bpp},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": hp.n_launches * args.steps, "clocks": sampler.summary(),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "cpu_baseline_1thread": cpu_1t,
+            "stock_gpu": stock_gpu, "dropin_eager": dropin_eager, "e2e": e2e,
+            "gpu_launches": hp.n_launches * args.steps * len(blocks), "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -623,6 +750,105 @@ def run_codec(args):
                               "msymbols_per_s": nsym * steps / dt_dec / 1e6, "round_trip_exact": roundtrip}}}), flush=True)
 
 
+def run_dropin(args):
+    """Secondary line: the UNMODIFIED reference ``DeepSVC`` (staged copy under the git-ignored
+    ``oracle/_ref``; conv transforms included) timed on the GPU stock -- torch ``grid_sample`` +
+    the oracle's eager compressai shim, i.e. the reference's own CUDA path -- and through
+    ``patch_reference()`` + ``swap_entropy_models()``.  ``--train``: one training step
+    (``Learner.py:1306-1343`` shape: B=8 256x256 crops, forward + backward + gradient sync) with the
+    data-parallel all-reduce of the model's real ``p.grad`` views overlapped with backward
+    (``shard.FlatGradBuckets``)."""
+    import torch
+    import deepsvc_b200 as dsvc
+    from deepsvc_b200 import _lib, shard
+    from oracle import stage_reference   # baseline leg: the reference itself
+    rank, local_rank, world = shard.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    if not stage_reference.available():
+        if rank == 0:
+            print(json.dumps({"workload": "dropin", "unavailable": "oracle/_ref not staged (run build() where /root/reference is mounted)"}))
+        return
+    _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    modules, image_model, video_model = stage_reference.import_reference()
+    torch.manual_seed(16)
+    model = video_model.DeepSVC().to(dev)
+    train = args.train
+    Bt, Hh, Ww = (8, 256, 256) if train else (1,) + tuple(frame_size(args))
+    g = torch.Generator().manual_seed(3 + rank)
+    ref = torch.rand(Bt, 3, Hh, Ww, generator=g).to(dev)
+    cur = (torch.roll(ref.cpu(), shifts=(2, -3), dims=(2, 3)) + 0.02 * torch.randn(Bt, 3, Hh, Ww, generator=g)).clamp(0, 1).to(dev)
+    sm = torch.rand(Bt, 256, Hh // 4, Ww // 4, generator=g).to(dev)
+    fea = (torch.randn(Bt, 64, Hh, Ww, generator=g) * 0.5).to(dev)
+    steps = min(args.steps, 30 if not train else 20)
+    buckets = None
+
+    def fwd():
+        with torch.no_grad():
+            return model(ref, cur, sm, fea)
+
+    def train_step():
+        for p_ in model.parameters():
+            p_.grad = None                      # optimizer.zero_grad(set_to_none=True), Learner.py:177
+        out = model(ref, cur, sm, fea)
+        loss = out[2] * 2048 + out[7] + model.aux_loss() * 0.0   # lambda * mse + bpp (Learner.py:1343 shape)
+        loss.backward()
+        if buckets is not None:
+            buckets.allreduce(clamp=1.0)        # waits the overlapped buckets; mean; clamp (Learner.py:1687-1691)
+
+    step = train_step if train else fwd
+    model.train(train)
+
+    def timed():
+        ms = time_gpu_eager(step, dev, steps=steps, warmup=3)
+        return shard.max_over_ranks(ms, dev)
+
+    def host_issue():
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        t = (time.perf_counter() - t0) / steps * 1e3
+        torch.cuda.synchronize(dev)
+        return t
+
+    if world > 1 and train:
+        buckets = shard.FlatGradBuckets(list(model.parameters()))
+    stock_ms = timed()
+    stock_host = host_issue()
+    if buckets is not None:
+        for h in buckets._hooks:
+            h.remove()
+    dsvc.patch_reference(modules, video_model, image_model)
+    n_swapped = dsvc.swap_entropy_models(model)
+    if world > 1 and train:
+        buckets = shard.FlatGradBuckets(list(model.parameters()))
+    patched_ms = timed()
+    patched_host = host_issue()
+    dsvc.unpatch_reference()
+    if rank == 0:
+        unit = "frame-steps/s" if train else "frames/s"
+        print(json.dumps({
+            "metric": ("reference DeepSVC training steps/sec (whole model, B=8 256x256)" if train else
+                       f"reference DeepSVC.forward frames/sec (whole model incl. conv transforms, {Ww}x{Hh})"),
+            "value": world * 1e3 / patched_ms, "unit": unit, "n_gpus": world, "steps": steps, "warmup": 3,
+            "ms_per_step": patched_ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ("unmodified reference video_model.DeepSVC (oracle/_ref), eager, random-init weights; "
+                                    + ("training step: forward + backward" + (" + FlatGradBuckets all-reduce of the model's "
+                                       f"{sum(p.numel() for p in model.parameters()) * 4 / 1e6:.1f} MB of gradients overlapped "
+                                       "with backward, mean + clamp" if world > 1 else "") if train else "inference forward")),
+                       "entropy_modules_swapped": n_swapped},
+            "stock_gpu": {"value": world * 1e3 / stock_ms, "unit": unit, "ms_per_step": stock_ms, "host_issue_ms": stock_host,
+                          "kind": "the same model unpatched: torch grid_sample + eager compressai shim"},
+            "patched": {"value": world * 1e3 / patched_ms, "unit": unit, "ms_per_step": patched_ms, "host_issue_ms": patched_host},
+            "speedup_vs_stock_gpu": stock_ms / patched_ms}), flush=True)
+    if world > 1:
+        torch.distributed.barrier(device_ids=[local_rank])
+        torch.distributed.destroy_process_group()
+
+
 def main():
     args = parse()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -640,6 +866,8 @@ def main():
         run_cfg4(args)
     elif args.workload == "codec":
         run_codec(args)
+    elif args.workload == "dropin":
+        run_dropin(args)
     else:
         run_ours(args)
 

@@ -82,9 +82,29 @@ def _require_cuda_f32(name, *tensors):
             raise RuntimeError(f"deepsvc_b200.{name}: fp32 tensors required, got {t.dtype}")
 
 
+STRICT_STRIDES = False  # True: raise on a layout the kernels cannot read in place (benchmarking)
+
+
+def _dense_rows(t: Tensor) -> bool:
+    return t.is_contiguous() or (t.dim() >= 2 and t.size(0) > 0 and t[0].is_contiguous())
+
+
+def _in_place_layout(t: Optional[Tensor], what: str) -> Optional[Tensor]:
+    """`t` itself when the kernels can read it in place (dense, or dense per batch row: the
+    memory shape of ``y.chunk(num_slices, 1)`` slices, image_model.py:164).  Any other view the
+    reference accepts -- e.g. the spatial crops ``mu[:, :, :h, :w]`` of image_model.py:171,175
+    on an unpadded input -- is copied once, like the stock eager ops would (STRICT_STRIDES
+    turns the copy into an error)."""
+    if t is None or _dense_rows(t):
+        return t
+    if STRICT_STRIDES:
+        raise RuntimeError(f"deepsvc_b200.{what}: unsupported strides (tensor must be contiguous, "
+                           "or contiguous per batch row) and STRICT_STRIDES is set")
+    return t.contiguous()
+
+
 def _rows_of(t: Tensor):
-    """(rows, inner, row_stride) of a tensor that is dense, or dense per batch row
-    (the memory shape of ``y.chunk(num_slices, 1)`` slices, image_model.py:164)."""
+    """(rows, inner, row_stride) of a tensor that is dense, or dense per batch row."""
     n = t.numel()
     if t.is_contiguous():
         return 1, n, n
@@ -92,7 +112,7 @@ def _rows_of(t: Tensor):
         inner = n // t.size(0)
         return t.size(0), inner, t.stride(0)
     raise RuntimeError("deepsvc_b200: unsupported strides (tensor must be contiguous, or "
-                       "contiguous per batch row); no silent layout copies are made")
+                       "contiguous per batch row)")
 
 
 def _common_rows(tensors):
@@ -117,6 +137,7 @@ def gc_launch(x, scales, means=None, noise=None, *, want_outputs=False, want_lik
               scale_table=None, scale_bound=0.11, lik_bound=1e-9):
     """One fused GaussianConditional launch (no autograd).  Returns a dict with the
     requested outputs: outputs, likelihood, y_hat, symbols, indexes, bits_partials."""
+    x, scales, means, noise = (_in_place_layout(t, "gaussian_conditional") for t in (x, scales, means, noise))
     ins = [t for t in (x, scales, means, noise) if t is not None]
     _require_cuda_f32("gaussian_conditional", *ins)
     rows, inner, st = _common_rows(ins)
@@ -168,6 +189,7 @@ class _GaussianConditionalFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, scales, means, noise, scale_bound, lik_bound, want_bits):
+        x, scales, means, noise = (_in_place_layout(t, "GaussianConditional") for t in (x, scales, means, noise))
         r = gc_launch(x, scales, means, noise, want_outputs=True, want_likelihood=True,
                       want_y_hat=True, want_bits=want_bits, scale_bound=scale_bound,
                       lik_bound=lik_bound)
@@ -243,6 +265,8 @@ class EntropyModel(nn.Module):
         self.register_buffer("_offset", torch.IntTensor())
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
+        self._tables_gen = 0        # bumped whenever the CDF buffers are replaced
+        self._tables_cache = None
 
     @property
     def offset(self):
@@ -302,11 +326,28 @@ class EntropyModel(nn.Module):
         if self._cdf_length.numel() == 0:
             raise ValueError("Uninitialized CDF lengths. Run update() first")
 
+    def _invalidate_tables(self):
+        self._tables_gen += 1
+        self._tables_cache = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._invalidate_tables()       # checkpoint CDFs replace the buffers' contents
+
+    def __setattr__(self, name, value):
+        # update_registered_buffers (image_model.py:304-317) and update() assign new buffers
+        if name in ("_quantized_cdf", "_offset", "_cdf_length") and "_tables_gen" in self.__dict__:
+            self.__dict__["_tables_gen"] += 1
+            self.__dict__["_tables_cache"] = None
+        super().__setattr__(name, value)
+
     def _cdf_tables(self):
+        """Host copy of the coder tables; keyed on a generation counter (addresses can be
+        recycled by the caching allocator) plus the buffers' in-place version counters."""
         from .ans import CdfTables
-        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version,
-               self._offset.data_ptr(), self._cdf_length.data_ptr())
-        if getattr(self, "_tables_cache", None) is None or self._tables_cache[0] != key:
+        key = (self._tables_gen, self._quantized_cdf._version, self._offset._version,
+               self._cdf_length._version)
+        if self._tables_cache is None or self._tables_cache[0] != key:
             self._tables_cache = (key, CdfTables(self._quantized_cdf, self._cdf_length, self._offset))
         return self._tables_cache[1]
 

@@ -219,11 +219,15 @@ class PFrameHotPath:
             else:
                 self.run()
         self._graph = g
+        self._graphs = getattr(self, "_graphs", {})
+        self._graphs["serial" if not dag else ("wide" if wide else "branches4")] = g
         self.dag = dag
         return g
 
-    def replay(self):
-        self._graph.replay()
+    def replay(self, which=None):
+        """Replay the last captured graph, or the one captured as `which`
+        ("wide" | "branches4" | "serial")."""
+        (self._graph if which is None else self._graphs[which]).replay()
 
     def results(self):
         """Outputs of the last run (device tensors) + bpp as python floats (synchronises)."""
@@ -233,6 +237,42 @@ class PFrameHotPath:
             r[f"{name}_y_hat"] = torch.cat(r[f"{name}_y_hat_slices"], 1)
         r["bpp_mv"], r["bpp_res"], r["bpp"] = bpp[0], bpp[1], bpp[0] + bpp[1]
         return r
+
+
+def pframe_eager(inputs: dict, models: dict) -> dict:
+    """One P-frame of the path issued EAGERLY through the package's public drop-in API, call for
+    call what an unmodified ``DeepSVC.forward`` executes after ``patch_reference()`` +
+    ``swap_entropy_models()`` (no pre-bound launches, no CUDA graph, likelihood tensors
+    materialised, the bit sums as the reference's own torch expression):
+    ``torch_warp`` x 6 (``modules.py:167,429``, ``video_model.py:37``); per codec
+    ``entropy_bottleneck(z)`` + ``ste_round`` (``image_model.py:155-162``), 8 x
+    (``gaussian_conditional(y, scale, mu)`` + ``ste_round(y - mu) + mu``, ``:181-183``), ``torch.cat``
+    (``:191``) and ``log().sum() / (-ln 2 * pixels)`` (``video_model.py:39-42``)."""
+    from .entropy import ste_round
+    from .warp import torch_warp
+    out = {"spynet": [torch_warp(im, fl) for im, fl in zip(inputs["pyr_img"], inputs["pyr_flow"])]}
+    out["warped_frame"] = torch_warp(inputs["ref_frame"], inputs["flow"])
+    out["warped_feature"] = torch_warp(inputs["feature"], inputs["flow"])
+    B, _, H, W = inputs["ref_frame"].shape
+    pixels = B * H * W
+    for name in ("mv", "res"):
+        eb, gc = models[name]
+        z = inputs[f"{name}_z"]
+        _, z_lik = eb(z)
+        z_off = eb._get_medians()
+        out[f"{name}_z_hat"] = ste_round(z - z_off) + z_off
+        y_hat_slices, y_lik = [], []
+        for y_s, s_s, m_s in zip(inputs[f"{name}_y"].chunk(NUM_SLICES, 1),
+                                 inputs[f"{name}_scales"].chunk(NUM_SLICES, 1),
+                                 inputs[f"{name}_means"].chunk(NUM_SLICES, 1)):
+            _, lik = gc(y_s, s_s, m_s)
+            y_lik.append(lik)
+            y_hat_slices.append(ste_round(y_s - m_s) + m_s)
+        out[f"{name}_y_hat"] = torch.cat(y_hat_slices, 1)
+        liks = {"y": torch.cat(y_lik, 1), "z": z_lik}
+        out[f"bpp_{name}"] = sum(torch.log(l).sum() / (-math.log(2) * pixels) for l in liks.values())
+    out["bpp"] = out["bpp_mv"] + out["bpp_res"]
+    return out
 
 
 class HostSession:

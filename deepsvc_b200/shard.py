@@ -167,45 +167,106 @@ def allreduce_gradients(params, bucket_bytes: int = 32 << 20, clamp: float = Non
 
 
 class FlatGradBuckets:
-    """The same reduction without the per-step gather/scatter copies: gradients LIVE in flat fp32
-    buckets (every ``p.grad`` is a view into one), so a step's sync is one in-place NCCL all-reduce
-    per bucket plus two elementwise passes (mean, clamp).  Create it once after the model is on
-    its device; backward passes then accumulate straight into the buckets."""
+    """The same reduction without the per-step gather/scatter copies, overlapped with backward
+    ("DDP buckets overlapped with backward"): gradients LIVE in flat fp32 buckets
+    (every ``p.grad`` is a view into one), and a post-accumulate-grad hook on every parameter
+    starts a bucket's in-place NCCL all-reduce the moment its last gradient of the step has
+    been written, while autograd is still producing the earlier layers' gradients.
+    ``allreduce()`` after ``backward()`` launches whatever has not been started (parameters
+    that received no gradient this step), waits, takes the mean and applies the reference's
+    element-wise clamp (``Learner.py:1687-1691``) AFTER the reduction.
 
-    def __init__(self, params, bucket_bytes: int = 32 << 20):
+    ``optimizer.zero_grad()`` defaults to ``set_to_none=True`` (the reference calls it at
+    ``Learner.py:177``), after which autograd allocates fresh ``.grad`` tensors: the hook (and
+    ``allreduce()``) copy such a gradient into its bucket view and re-bind ``p.grad`` to the
+    view, so the views survive any ``zero_grad`` flavour.  Create it once after the model is
+    on its device."""
+
+    def __init__(self, params, bucket_bytes: int = 32 << 20, overlap: bool = True):
         self.params = [p for p in params if p.requires_grad]
-        self.buckets = []
+        self.buckets, self._views, self._bucket_of = [], {}, {}
+        self._members = []
         cur, size = [], 0
         for p in self.params:
             cur.append(p)
             size += p.numel() * 4
             if size >= bucket_bytes:
-                self.buckets.append(self._make(cur))
+                self._make(cur)
                 cur, size = [], 0
         if cur:
-            self.buckets.append(self._make(cur))
+            self._make(cur)
+        self._ready = [0] * len(self.buckets)
+        self._seen = set()
+        self._works = [None] * len(self.buckets)
+        self.overlap = overlap
+        self._hooks = []
+        if overlap:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
-    @staticmethod
-    def _make(ps):
+    def _make(self, ps):
         flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
         off = 0
+        bi = len(self.buckets)
         for p in ps:
             n = p.numel()
             view = flat[off:off + n].view_as(p)
             if p.grad is not None:
                 view.copy_(p.grad)
             p.grad = view
+            self._views[id(p)] = view
+            self._bucket_of[id(p)] = bi
             off += n
-        return flat
+        self.buckets.append(flat)
+        self._members.append(list(ps))
+
+    def _rebind(self, p) -> None:
+        """Make ``p.grad`` the bucket view again (after ``zero_grad(set_to_none=True)`` autograd
+        allocated a fresh tensor; after ``p.grad = None`` with no new gradient the view is zeroed)."""
+        view = self._views[id(p)]
+        g = p.grad
+        if g is None:
+            view.zero_()
+        elif g.data_ptr() != view.data_ptr():
+            view.copy_(g)
+        else:
+            return
+        p.grad = view
+
+    def _launch(self, bi: int) -> None:
+        if self._works[bi] is not None:
+            return
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        self._works[bi] = (dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, async_op=True)
+                           if world > 1 else True)
+
+    def _on_grad(self, p) -> None:
+        if id(p) in self._seen:   # a second accumulation in the same step (shared parameter)
+            return
+        self._seen.add(id(p))
+        self._rebind(p)
+        bi = self._bucket_of[id(p)]
+        self._ready[bi] += 1
+        if self._ready[bi] == len(self._members[bi]):
+            self._launch(bi)
 
     def allreduce(self, clamp: float = None) -> int:
         world = dist.get_world_size() if dist.is_initialized() else 1
-        works = [dist.all_reduce(f, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
-                 for f in self.buckets]
-        for f, w in zip(self.buckets, works):
-            if w is not None:
+        for bi, ps in enumerate(self._members):
+            if self._works[bi] is None:
+                for p in ps:
+                    if id(p) not in self._seen:
+                        self._rebind(p)
+                self._launch(bi)
+        for bi, f in enumerate(self.buckets):
+            w = self._works[bi]
+            if w is not True:
                 w.wait()
+            if world > 1:
                 f.div_(world)
             if clamp is not None:  # after the reduction (Learner.py:1687-1691 on the reduced gradient)
                 f.clamp_(-clamp, clamp)
+        self._ready = [0] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+        self._seen.clear()
         return len(self.buckets)

@@ -90,8 +90,6 @@ def _check(inp, flow):
     if inp.size(0) != flow.size(0) or inp.shape[2:] != flow.shape[2:]:
         raise RuntimeError(
             f"deepsvc_b200.torch_warp: shape mismatch {tuple(inp.shape)} vs {tuple(flow.shape)}")
-    if not flow.is_contiguous():
-        raise RuntimeError("deepsvc_b200.torch_warp: flow must be contiguous NCHW")
 
 
 def _layout_of(inp):
@@ -103,9 +101,36 @@ def _layout_of(inp):
                        "channels_last with C % 4 == 0 (no silent layout copies)")
 
 
+STRICT_STRIDES = False  # True: raise instead of copying a layout the kernels cannot read in place
+
+
+def _dense(inp, flow):
+    """The reference accepts any strides (``F.grid_sample`` does); the kernels read dense NCHW
+    (or channels_last with C % 4 == 0).  Anything else is copied once, as the stock op's own
+    ``.contiguous()`` would, unless STRICT_STRIDES asks for an error."""
+    if not flow.is_contiguous():
+        if STRICT_STRIDES:
+            raise RuntimeError("deepsvc_b200.torch_warp: flow must be contiguous NCHW")
+        flow = flow.contiguous()
+    if not (inp.is_contiguous() or (inp.is_contiguous(memory_format=torch.channels_last)
+                                    and inp.size(1) % 4 == 0)):
+        if STRICT_STRIDES:
+            raise RuntimeError("deepsvc_b200.torch_warp: input must be contiguous NCHW, or "
+                               "channels_last with C % 4 == 0")
+        inp = inp.contiguous()
+    return inp, flow
+
+
+def _drop_workspace(device):
+    """A failed launch may leave the scheduler words non-zero: forget the cached buffers."""
+    for key in [k for k in _ws_cache if k[0] == device]:
+        del _ws_cache[key]
+
+
 def warp_forward(inp, flow, flow_mode=None, algo=None):
     """Raw forward launch (no autograd)."""
     _check(inp, flow)
+    inp, flow = _dense(inp, flow)
     layout = _layout_of(inp)
     B, C, H, W = inp.shape
     out = torch.empty_like(inp)  # preserves NCHW / channels_last
@@ -122,6 +147,8 @@ def warp_forward(inp, flow, flow_mode=None, algo=None):
             _flow_mode if flow_mode is None else flow_mode, layout,
             _algo if algo is None else algo, _lib.ptr(ws), 0 if ws is None else ws.numel(),
             _lib.stream_ptr(inp.device))
+    if err:
+        _drop_workspace(inp.device)
     _lib.check(err, "dsvc_warp_fwd_f32")
     return out
 
@@ -150,6 +177,8 @@ def warp_forward2(inp_a, inp_b, flow, flow_mode=None):
             B, Ca, Cb, H, W, lin_x.data_ptr(), lin_y.data_ptr(), sx, sy, inv_sx, inv_sy,
             _flow_mode if flow_mode is None else flow_mode, _lib.ptr(ws), ws.numel(),
             _lib.stream_ptr(inp_a.device))
+    if err:
+        _drop_workspace(inp_a.device)
     _lib.check(err, "dsvc_warp_fwd2_f32")
     return out_a, out_b
 
@@ -157,8 +186,16 @@ def warp_forward2(inp_a, inp_b, flow, flow_mode=None):
 def warp_backward(grad_out, inp, flow, need_input_grad=True, need_flow_grad=True, flow_mode=None):
     """Raw backward launch: returns (grad_input | None, grad_flow | None)."""
     _check(inp, flow)
+    if not flow.is_contiguous():
+        flow = flow.contiguous()
     if not inp.is_contiguous():
-        raise RuntimeError("deepsvc_b200.torch_warp backward: contiguous NCHW input required")
+        # channels_last forward inputs: the backward kernels are NCHW (one copy; the gradient
+        # comes back in the input's memory format)
+        gin, gflow = warp_backward(grad_out, inp.contiguous(), flow, need_input_grad, need_flow_grad, flow_mode)
+        if gin is not None:
+            gin = gin.contiguous(memory_format=torch.channels_last) if inp.is_contiguous(
+                memory_format=torch.channels_last) else gin
+        return gin, gflow
     grad_out = grad_out.contiguous()
     B, C, H, W = inp.shape
     gin = torch.zeros_like(inp) if need_input_grad else None

@@ -39,13 +39,17 @@ def oracle():
 
 @pytest.fixture(scope="session")
 def reference_modules():
-    """The unmodified reference, importable only in the build container."""
-    if not os.path.isdir(REFERENCE):
-        pytest.skip("/root/reference not mounted (GPU box)")
+    """The unmodified reference: /root/reference in the build container, the byte-identical
+    copy staged by ``oracle/stage_reference.py`` into the git-ignored ``oracle/_ref/`` on the GPU box."""
     from oracle import reference_ops  # noqa: F401  (puts oracle/shim on sys.path)
-    if REFERENCE not in sys.path:
-        sys.path.insert(0, REFERENCE)
-    import modules
-    import image_model
-    import video_model
-    return modules, image_model, video_model
+    from oracle import stage_reference
+    if os.path.isdir(REFERENCE):
+        if REFERENCE not in sys.path:
+            sys.path.insert(0, REFERENCE)
+        import modules
+        import image_model
+        import video_model
+        return modules, image_model, video_model
+    if not stage_reference.available():
+        pytest.skip("reference neither mounted nor staged under oracle/_ref")
+    return stage_reference.import_reference()

@@ -167,9 +167,29 @@ def test_channels_last(oracle):
         d.set_flow_arithmetic("cuda")
     assert out.is_contiguous(memory_format=torch.channels_last)
     assert_warp_close(out, ref, "nhwc")
+    # strides the kernels cannot read in place: copied once (the reference's grid_sample accepts
+    # them), an error in strict mode; a non-contiguous flow likewise
+    from deepsvc_b200 import warp as Wm
     bad = torch.randn(1, 3, 8, 8).to(_dev()).contiguous(memory_format=torch.channels_last)
-    with pytest.raises(RuntimeError, match="layout"):
-        d.torch_warp(bad[:, :, ::2], torch.zeros(1, 2, 4, 8, device=_dev()))
+    fl = (torch.randn(1, 2, 4, 16, generator=g) * 2).to(_dev())
+    got = d.torch_warp(bad[:, :, ::2], fl[:, :, :, ::2])
+    assert_warp_close(got, oracle.torch_warp(bad[:, :, ::2].contiguous(), fl[:, :, :, ::2].contiguous()), "strided")
+    Wm.STRICT_STRIDES = True
+    try:
+        with pytest.raises(RuntimeError, match="contiguous"):
+            d.torch_warp(bad[:, :, ::2], torch.zeros(1, 2, 4, 8, device=_dev()))
+    finally:
+        Wm.STRICT_STRIDES = False
+    # channels_last input through autograd: gradients come back in the input's memory format
+    xg = x.clone().requires_grad_(True)
+    fg = flow.to(_dev()).clone().requires_grad_(True)
+    xr = inp.to(_dev()).clone().requires_grad_(True)
+    fr = flow.to(_dev()).clone().requires_grad_(True)
+    cot = torch.randn(2, 64, 48, 80, generator=g).to(_dev())
+    d.torch_warp(xg, fg).backward(cot.contiguous(memory_format=torch.channels_last))
+    d.torch_warp(xr, fr).backward(cot)
+    assert xg.grad.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(xg.grad, xr.grad, rtol=1e-4, atol=1e-5) and torch.allclose(fg.grad, fr.grad, rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "warp_*.npz"))))

@@ -85,9 +85,34 @@ for p in params2:
 fb = shard.FlatGradBuckets(params2, bucket_bytes=16)
 nb2 = fb.allreduce(clamp=1.0)
 params2[1].grad.add_(1.0)                      # grads are views of the buckets
+# a real model: backward -> zero_grad() (set_to_none=True, Learner.py:177) -> backward -> allreduce.
+# The second backward allocates fresh .grad tensors; the buckets must still reduce THEM.
+torch.manual_seed(1)
+net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Tanh(), torch.nn.Linear(3, 2))
+unused = torch.nn.Parameter(torch.ones(2))     # receives no gradient
+fb3 = shard.FlatGradBuckets(list(net.parameters()) + [unused], bucket_bytes=32)
+opt = torch.optim.SGD(list(net.parameters()) + [unused], lr=0.1)
+x = torch.arange(8.0).reshape(2, 4) * (rank + 1)
+net(x).sum().backward()
+fb3.allreduce()
+opt.zero_grad()                                # grads -> None
+assert net[0].weight.grad is None
+import copy
+twin = copy.deepcopy(net)                      # the same step without buckets: this rank's own gradients
+twin(x * 0.5).pow(2).sum().backward()
+local = [p.grad.clone() for p in twin.parameters()]
+net(x * 0.5).pow(2).sum().backward()           # hooks re-bind the fresh grads and start the buckets
+fb3.allreduce()
+gathered = [None, None]
+dist.all_gather_object(gathered, [g.tolist() for g in local])
+want = [((torch.tensor(a) + torch.tensor(b)) / 2) for a, b in zip(*gathered)]
+ddp_ok = all(torch.allclose(p.grad, w, atol=1e-6) for p, w in zip(net.parameters(), want))
+views_ok = all(p.grad.data_ptr() == fb3._views[id(p)].data_ptr() for p in net.parameters())
+unused_zero = bool((fb3._views[id(unused)] == 0).all())
 out = {"rank": rank, "frames": frames, "tmax": tmax, "total": total, "all": allm,
        "g0": params[0].grad.tolist(), "buckets": nb,
-       "f0": params2[0].grad.tolist(), "f1_in_bucket": fb.buckets[1].tolist(), "fbuckets": nb2}
+       "f0": params2[0].grad.tolist(), "f1_in_bucket": fb.buckets[1].tolist(), "fbuckets": nb2,
+       "ddp_ok": ddp_ok, "views_ok": views_ok, "unused_zero": unused_zero}
 if rank == 0:
     print("RESULT " + json.dumps(out), flush=True)
 dist.barrier()
@@ -116,3 +141,5 @@ def test_world_size_2_gloo(tmp_path):
     assert out["buckets"] == 2
     assert out["f0"] == [0.375] * 5 and out["fbuckets"] == 2     # mean(0.25, 0.5), in place
     assert out["f1_in_bucket"] == [1.375] * 6                     # p.grad is a view of its bucket
+    # backward -> zero_grad(set_to_none) -> backward -> allreduce reduces the step's real gradients
+    assert out["ddp_ok"] and out["views_ok"] and out["unused_zero"]
