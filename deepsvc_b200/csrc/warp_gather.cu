@@ -342,7 +342,7 @@ extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
 
 static int g_bwd_algo = -1;  // DSVC_WARP_BWD_* (tests / profiling; default from $DSVC_BWD_ALGO)
 extern "C" int dsvc_set_warp_bwd_algo(int algo) {
-    DSVC_CHECK_ARG(algo >= 0 && algo <= 2);
+    DSVC_CHECK_ARG(algo >= 0 && algo <= 3);
     g_bwd_algo = algo;
     return 0;
 }
@@ -360,7 +360,7 @@ extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, cons
     WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
     // 0 = auto (staged kernel when the shape is eligible), 1 = per-pixel kernel, 2 = staged forced
     if (g_bwd_algo < 0) { const char* e = getenv("DSVC_BWD_ALGO"); g_bwd_algo = e ? atoi(e) : 0; }
-    const int algo = g_bwd_algo;
+    const int algo = g_bwd_algo == 3 ? 0 : g_bwd_algo;
     if (algo != 1) {
         const int r = dsvc_warp_bwd_staged_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p,
                                                   algo == 2, st);
@@ -375,4 +375,40 @@ extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, cons
     else
         warp_bwd_nchw<false, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
     DSVC_RETURN_LAST();
+}
+
+size_t dsvc_warp_bwd_gather_workspace(int B, int H, int W);  // warp_bwd_gather.cu
+int dsvc_warp_bwd_gather_launch(const float* gout, const float* input, const float* flow, float* gin,
+                                float* gflow, const float* lin_x, const float* lin_y, const WarpParams& p,
+                                bool force, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+extern "C" size_t dsvc_warp_bwd_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return dsvc_warp_bwd_gather_workspace(B, H, W);
+}
+
+extern "C" int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, const float* flow,
+                                    float* grad_input, float* grad_flow, int B, int C, int H, int W,
+                                    const float* lin_x, const float* lin_y, float sx, float sy,
+                                    float inv_sx, float inv_sy, int flow_mode, int layout,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    DSVC_CHECK_ARG(warp_args_ok(grad_out, input, flow, B, C, H, W, lin_x, lin_y));
+    DSVC_CHECK_ARG(flow_mode == 0 || flow_mode == 1);
+    DSVC_CHECK_ARG(layout == DSVC_LAYOUT_NCHW);
+    if (!grad_input && !grad_flow) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g_bwd_algo < 0) { const char* e = getenv("DSVC_BWD_ALGO"); g_bwd_algo = e ? atoi(e) : 0; }
+    if (grad_input && (g_bwd_algo == 0 || g_bwd_algo == 3)) {
+        WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+        const int r = dsvc_warp_bwd_gather_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p,
+                                                  g_bwd_algo == 3, workspace, workspace_bytes, st);
+        if (r != -1) return r;
+        if (g_bwd_algo == 3) return (int)cudaErrorInvalidValue;
+    }
+    if (grad_input) {
+        const cudaError_t e = cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return dsvc_warp_bwd_f32(grad_out, input, flow, grad_input, grad_flow, B, C, H, W, lin_x, lin_y, sx, sy, inv_sx,
+                             inv_sy, flow_mode, layout, stream);
 }

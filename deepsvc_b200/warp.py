@@ -198,21 +198,41 @@ def warp_backward(grad_out, inp, flow, need_input_grad=True, need_flow_grad=True
         return gin, gflow
     grad_out = grad_out.contiguous()
     B, C, H, W = inp.shape
-    gin = torch.zeros_like(inp) if need_input_grad else None
+    # neither gradient needs initialising: the gather kernel writes every element of grad_input
+    # once, the other kernels zero-fill it inside dsvc_warp_bwd_ws_f32
+    gin = torch.empty_like(inp) if need_input_grad else None
     gflow = torch.empty_like(flow) if need_flow_grad else None
     if inp.numel() == 0 or not (need_input_grad or need_flow_grad):
         return gin, gflow
     lin_x, lin_y = _base_grids(inp.device, H, W)
     sx, sy, inv_sx, inv_sy = _scales(H, W)
     lib = _lib.load()
+    ws = _bwd_workspace(inp.device, B, H, W) if need_input_grad else None
     with torch.cuda.device(inp.device):
-        err = lib.dsvc_warp_bwd_f32(
+        err = lib.dsvc_warp_bwd_ws_f32(
             grad_out.data_ptr(), inp.data_ptr(), flow.data_ptr(), _lib.ptr(gin), _lib.ptr(gflow),
             B, C, H, W, lin_x.data_ptr(), lin_y.data_ptr(), sx, sy, inv_sx, inv_sy,
             _flow_mode if flow_mode is None else flow_mode, _lib.LAYOUT_NCHW,
-            _lib.stream_ptr(inp.device))
-    _lib.check(err, "dsvc_warp_bwd_f32")
+            _lib.ptr(ws), 0 if ws is None else ws.numel(), _lib.stream_ptr(inp.device))
+    _lib.check(err, "dsvc_warp_bwd_ws_f32")
     return gin, gflow
+
+
+_bwd_ws_cache = {}
+
+
+def _bwd_workspace(device, B, H, W):
+    """Per-tile flag bytes of the gather backward (written before they are read inside one
+    call): one buffer per (device, stream), a fresh one under CUDA-graph capture."""
+    n = _lib.load().dsvc_warp_bwd_workspace_bytes(B, H, W)
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(n, dtype=torch.uint8, device=device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _bwd_ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 1 << 14), dtype=torch.uint8, device=device)
+        _bwd_ws_cache[key] = ws
+    return ws
 
 
 class _WarpFn(torch.autograd.Function):

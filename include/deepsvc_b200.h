@@ -107,6 +107,24 @@ int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* fl
                       float sx, float sy, float inv_sx, float inv_sy,
                       int flow_mode, int layout, void* stream);
 
+/* The same gradient with a caller-provided workspace: NEITHER output needs initialising.
+ * With `workspace` (>= dsvc_warp_bwd_workspace_bytes(B,H,W) bytes, any contents; one flag
+ * byte per 64 x 16 tile, written before it is read) and an eligible shape (grad_input wanted,
+ * C >= 8, W % 4 == 0, W >= 64, H >= 16, 16-byte aligned pointers) grad_input is produced by
+ * the destination-owned gather kernel (csrc/warp_bwd_gather.cu: per-tile tap lists in
+ * registers, TMA-staged grad_out box, one plain store per element, no atomics) followed by a
+ * fix-up launch for the taps outside a tile's search region.  Otherwise grad_input is
+ * zero-filled here and dsvc_warp_bwd_f32 runs.  DSVC_WARP_BWD_GATHER (3) forces the gather
+ * kernel (cudaErrorInvalidValue if the shape is not eligible). */
+int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, const float* flow,
+                         float* grad_input, float* grad_flow,
+                         int B, int C, int H, int W,
+                         const float* lin_x, const float* lin_y,
+                         float sx, float sy, float inv_sx, float inv_sy,
+                         int flow_mode, int layout,
+                         void* workspace, size_t workspace_bytes, void* stream);
+size_t dsvc_warp_bwd_workspace_bytes(int B, int H, int W);
+
 /* Fusions around the few-channel (C <= 4) warps -- SURVEY.md 8f-3, inference only.
  * Exactly one of `flow` [B,2,H,W] and `flow_coarse` [B,2,H/2,W/2] is given.
  *  - flow_coarse: the SpyNet level of modules.py:163-168.  flow_up [B,2,H,W] is written
@@ -138,6 +156,7 @@ int dsvc_blend_f32(const float* weight, const float* warped, const float* pred, 
 #define DSVC_WARP_BWD_AUTO 0
 #define DSVC_WARP_BWD_DIRECT 1
 #define DSVC_WARP_BWD_STAGED 2
+#define DSVC_WARP_BWD_GATHER 3 /* dsvc_warp_bwd_ws_f32 only */
 int dsvc_set_warp_bwd_algo(int algo);
 
 /* Number of double partial sums a gc launch over rows x inner elements writes. */

@@ -1,0 +1,77 @@
+"""GPU check + timing of the warp backward kernels (direct / staged / gather) against each other.
+usage: python scripts/check_bwd.py [--small] [--time]"""
+import os
+import sys
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deepsvc_b200 import _lib, synthetic  # noqa: E402
+from deepsvc_b200.warp import warp_backward  # noqa: E402
+
+dev = torch.device("cuda:0")
+lib = _lib.load()
+ALGOS = {"direct": _lib.WARP_BWD_DIRECT, "staged": _lib.WARP_BWD_STAGED, "gather": _lib.WARP_BWD_GATHER}
+
+
+def run(algo, gout, inp, flow, gi=True, gf=True):
+    _lib.check(lib.dsvc_set_warp_bwd_algo(ALGOS[algo]), "algo")
+    try:
+        return warp_backward(gout, inp, flow, gi, gf)
+    finally:
+        lib.dsvc_set_warp_bwd_algo(0)
+
+
+def check(shape, kind, seed=0):
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(seed + H + W)
+    inp = torch.randn(B, C, H, W, generator=g).to(dev)
+    flow = synthetic.make_flow(kind, B, H, W, g).to(dev)
+    gout = torch.randn(B, C, H, W, generator=g).to(dev)
+    ref = run("direct", gout, inp, flow)
+    got = run("gather", gout, inp, flow)
+    torch.cuda.synchronize()
+    out = []
+    for a, b in zip(got, ref):
+        out.append((a - b).abs().max().item() / max(1.0, b.abs().max().item()))
+    got2 = run("gather", gout, inp, flow, True, False)
+    out.append((got2[0] - ref[0]).abs().max().item() / max(1.0, ref[0].abs().max().item()))
+    print(f"{shape} {kind}: rel err gin {out[0]:.2e} gflow {out[1]:.2e} gin-only {out[2]:.2e}", flush=True)
+    return max(out)
+
+
+def timeit(shape, kind, algos=("direct", "staged", "gather"), n=10):
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    inp = torch.randn(B, C, H, W, generator=g).to(dev)
+    flow = synthetic.make_flow(kind, B, H, W, g).to(dev)
+    gout = torch.randn(B, C, H, W, generator=g).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    nbytes = 4 * B * H * W * (3 * C + 4)
+    for a in algos:
+        ts = []
+        for _ in range(n):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(a, gout, inp, flow)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        print(f"time {shape} {kind} {a}: {ms * 1e3:.1f} us (incl. allocation / zero-fill)  {nbytes / ms / 1e6:.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    worst = 0.0
+    small = [((1, 8, 32, 64), "smooth"), ((2, 16, 40, 64), "smooth"), ((1, 9, 33, 100), "border"), ((1, 8, 16, 68), "stress")]
+    full = small + [((1, 64, 128, 192), k) for k in ("smooth", "stress", "border")] + \
+        [((8, 64, 64, 64), "smooth"), ((2, 16, 272, 480), "smooth"), ((1, 64, 1088, 1920), "smooth")]
+    for shape, kind in (small if "--small" in sys.argv else full):
+        worst = max(worst, check(shape, kind))
+    print("worst rel err", worst)
+    if "--time" in sys.argv:
+        timeit((1, 64, 1088, 1920), "smooth")
+        timeit((8, 64, 256, 256), "smooth")
+        timeit((1, 64, 1088, 1920), "stress", n=3)
+    sys.exit(0 if worst <= 1e-4 else 1)

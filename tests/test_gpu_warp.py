@@ -317,9 +317,10 @@ def _bwd_algo(algo):
 @pytest.mark.parametrize("kind", ["smooth", "stress", "border"])
 @pytest.mark.parametrize("shape", [(2, 16, 40, 64), (1, 64, 128, 192), (8, 64, 64, 64), (1, 9, 33, 100),
                                    (1, 8, 16, 68)])
-def test_backward_staged_vs_stock_torch_cuda(oracle, shape, kind, need):
-    """The staged backward (forced) against autograd of the reference function on the GPU
-    (its GPU branch, modules.py:44-62): gradients within 1e-4 of the tensor's scale."""
+@pytest.mark.parametrize("bwd", ["staged", "gather"])
+def test_backward_staged_vs_stock_torch_cuda(oracle, shape, kind, need, bwd):
+    """The staged / gather backward kernels (forced) against autograd of the reference function on
+    the GPU (its GPU branch, modules.py:44-62): gradients within 1e-4 of the tensor's scale."""
     import deepsvc_b200 as d
     from deepsvc_b200 import _lib, synthetic
     B, C, H, W = shape
@@ -328,7 +329,10 @@ def test_backward_staged_vs_stock_torch_cuda(oracle, shape, kind, need):
     flow0 = synthetic.make_flow(kind, B, H, W, g).to(_dev())
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     res = []
-    for fn, algo in ((oracle.torch_warp, _lib.WARP_BWD_AUTO), (d.torch_warp, _lib.WARP_BWD_STAGED)):
+    if bwd == "gather" and not need[0]:
+        pytest.skip("the gather kernel produces grad_input; flow-only gradients use the other kernels")
+    forced = _lib.WARP_BWD_STAGED if bwd == "staged" else _lib.WARP_BWD_GATHER
+    for fn, algo in ((oracle.torch_warp, _lib.WARP_BWD_AUTO), (d.torch_warp, forced)):
         _bwd_algo(algo)
         try:
             inp = inp0.clone().requires_grad_(need[0])
@@ -356,7 +360,8 @@ def test_backward_staged_matches_direct_kernel():
     flow = synthetic.smooth_flow(B, H, W, g).to(_dev())
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     out = {}
-    for name, algo in (("direct", _lib.WARP_BWD_DIRECT), ("staged", _lib.WARP_BWD_STAGED)):
+    for name, algo in (("direct", _lib.WARP_BWD_DIRECT), ("staged", _lib.WARP_BWD_STAGED),
+                       ("gather", _lib.WARP_BWD_GATHER)):
         _bwd_algo(algo)
         try:
             out[name] = warp_backward(gout, inp, flow, True, True)
@@ -366,9 +371,10 @@ def test_backward_staged_matches_direct_kernel():
         # bilinear weights of a pixel sum to 1: every plane of grad_input sums to H*W
         s = ones.double().sum((2, 3))
         assert (s - H * W).abs().max().item() <= 1e-3 * H * W, name
-    for a, b, nm in zip(out["staged"], out["direct"], ("grad_input", "grad_flow")):
-        err = (a - b).abs().max().item()
-        assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{nm} {err}"
+    for which in ("staged", "gather"):
+        for a, b, nm in zip(out[which], out["direct"], ("grad_input", "grad_flow")):
+            err = (a - b).abs().max().item()
+            assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{which} {nm} {err}"
 
 
 def test_backward_staged_collapsed_flow():
@@ -385,7 +391,7 @@ def test_backward_staged_collapsed_flow():
     flow0 = flow0.to(_dev())
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     res = []
-    for algo in (_lib.WARP_BWD_DIRECT, _lib.WARP_BWD_STAGED):
+    for algo in (_lib.WARP_BWD_DIRECT, _lib.WARP_BWD_STAGED, _lib.WARP_BWD_GATHER):
         _bwd_algo(algo)
         try:
             inp = inp0.clone().requires_grad_(True)
@@ -394,8 +400,9 @@ def test_backward_staged_collapsed_flow():
             res.append((inp.grad, flow.grad))
         finally:
             _bwd_algo(_lib.WARP_BWD_AUTO)
-    for a, b in zip(res[1], res[0]):
-        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+    for r in res[1:]:
+        for a, b in zip(r, res[0]):
+            assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
 
 
 def test_full_size_4k_forward_and_backward_properties(oracle):
