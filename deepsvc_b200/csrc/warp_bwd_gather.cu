@@ -50,7 +50,8 @@ constexpr int K = 8;                          // register slots per destination 
 constexpr int OVF = 2048;                     // later pairs of a tile (shared-memory list)
 constexpr int NS = 3;                         // load stages
 constexpr int STAGE_G = GBW * GBH, STAGE_IN = IBW * IBH;
-constexpr int G_BYTES = STAGE_G * 4, IN_BYTES = STAGE_IN * 4;
+constexpr int G_BYTES = STAGE_G * 4 + 128, IN_BYTES = STAGE_IN * 4;  // grad_out box + a zero word (unused list slots)
+constexpr int ZERO_OFF = STAGE_G * 4;         // the zero word of a stage, relative to its grad_out box
 constexpr int IN_OFF = NS * G_BYTES;          // dynamic smem: [NS grad_out boxes][NS input boxes][list]
 constexpr int OVF_OFF = IN_OFF + NS * IN_BYTES;
 constexpr size_t SMEM_BYTES = (size_t)OVF_OFF + (size_t)OVF * 8;
@@ -290,9 +291,10 @@ warp_bwd_gather_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
         return gsm0 + 4u * (uint32_t)((sy0 + ry - gby0) * GBW + (sx0 + rx - gbx0));
     };
     float pw[PPT][K];
-    uint32_t pa[PPT][K / 2];   // two 16-bit shared-window addresses per register
-    uint32_t slots = 0;        // bit d * K + j: pair j of element d is in use
+    uint32_t pa[PPT][K / 2];   // two 16-bit shared-window addresses per register (stage 0)
     uint32_t ov[PPT];          // later pairs: first << 16 | count
+    // an unused slot reads its stage's zero word with weight 0: no predicates in the channel loop
+    const uint32_t zaddr = gsm0 + (uint32_t)ZERO_OFF;
 #pragma unroll
     for (int d = 0; d < PPT; ++d) {
         const int e = (warp * 2 + (d >> 1)) * TW + (d & 1) * 32 + lane;
@@ -301,11 +303,10 @@ warp_bwd_gather_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             float w = 0.0f;
-            uint32_t a = gsm0;
+            uint32_t a = zaddr;
             if (j < n) {
                 w = ellw[j * NE + e];
                 a = box_addr(ellq[j * NE + e]);
-                slots |= 1u << (d * K + j);
             }
             pw[d][j] = w;
             if (j & 1) pa[d][j >> 1] |= a << 16;
@@ -320,6 +321,8 @@ warp_bwd_gather_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
         ovf[obase[e] + r] = make_uint2(pr.x, box_addr(pr.y & 8191u));
     }
     __syncthreads();  // the build scratch is dead: the load stages may be overwritten
+    if (tid < NS) *reinterpret_cast<float*>(smem_raw + tid * G_BYTES + ZERO_OFF) = 0.0f;
+    __syncthreads();
 
     // ---- channel loop
     const int gchunks = (gbh + ROWCHUNK - 1) / ROWCHUNK;
@@ -365,23 +368,23 @@ warp_bwd_gather_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
     float* gi_ptr = gin + (size_t)plane0 * plane + pix0;
     const float* go_ptr = gout + (size_t)(plane0 + 1) * plane + pix0;  // own pixels, next channel
 
-    auto channel = [&](auto stc, int i) {
-        constexpr int ST = decltype(stc)::value;
-        constexpr int GOFF = ST * G_BYTES, IOFF = ST * IN_BYTES;
-        // (opaque to the optimiser: the unpacked addresses / steps / predicates are re-derived per
-        // channel instead of being hoisted into ~50 more registers)
-        asm volatile("" : "+r"(tapbits), "+r"(slots));
-#pragma unroll
-        for (int d = 0; d < PPT; ++d)
-#pragma unroll
-            for (int h = 0; h < K / 2; ++h) asm volatile("" : "+r"(pa[d][h]));
-        tma::mbar_wait(full0 + 8u * ST, (uint32_t)(i / NS) & 1u);
+    // one loop body for all stages (stage offsets are run-time values: the unrolled-by-stage body
+    // was 3 x ~450 instructions and 25 % of the stall samples were instruction fetches)
+#pragma unroll 1
+    for (int i = 0; i < nch; ++i) {
+        const uint32_t st = (uint32_t)(i % NS);
+        const uint32_t goff = st * (uint32_t)G_BYTES, ioff = st * (uint32_t)IN_BYTES;
+        // (opaque to the optimiser: unpacked addresses / steps are re-derived per channel instead
+        // of being hoisted into ~50 more registers)
+        asm volatile("" : "+r"(tapbits));
+        tma::mbar_wait(full0 + 8u * st, (uint32_t)(i / NS) & 1u);
         if (NEED_GFLOW) {
-            tma::static_for<PPT>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
                 const uint32_t dx = (tapbits >> k) & 1u ? 4u : 0u, dy = (tapbits >> (4 + k)) & 1u ? 4u * IBW : 0u;
-                const float v_nw = lds_i<IOFF>(a_n[k]), v_ne = lds_i<IOFF>(a_n[k] + dx);
-                const float v_sw = lds_i<IOFF>(a_n[k] + dy), v_se = lds_i<IOFF>(a_n[k] + dy + dx);
+                const uint32_t an = a_n[k] + ioff;
+                const float v_nw = lds(an), v_ne = lds(an + dx);
+                const float v_sw = lds(an + dy), v_se = lds(an + dy + dx);
                 // a tap outside the image re-reads its in-image neighbour with a zero 1-D weight
                 const float wx0 = __fsub_rn(1.0f, wx1[k]), wy0 = __fsub_rn(1.0f, wy1[k]);
                 const float tx = fmaf(wy1[k], v_se - v_sw, wy0 * (v_ne - v_nw));
@@ -391,37 +394,53 @@ warp_bwd_gather_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
                 // grad_out of the own pixel for the next channel: in flight during the gathers below
                 gcur[k] = ((tapbits >> (8 + k)) & 1u) && i + 1 < nch
                               ? ldg_stream(go_ptr + (size_t)(k >> 1) * p.W + (k & 1) * 32) : 0.0f;
-            });
+            }
             go_ptr += plane;
         }
-        // grad_input: every element's list, summed in list order, stored once
-        tma::static_for<PPT>([&](auto dc) {
-            constexpr int d = decltype(dc)::value;
-            float acc = 0.0f;
+        // grad_input: every element's list, summed in list order, stored once.  The stage offset is
+        // added to both 16-bit halves of a packed address pair at once (no carry: < 64 KB).
+        const uint32_t goff2 = goff * 0x10001u;
+        float acc[PPT];
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const uint32_t a = (j & 1) ? pa[d][j >> 1] >> 16 : pa[d][j >> 1] & 0xffffu;
-                if ((slots >> (d * K + j)) & 1u) acc = fmaf(pw[d][j], lds_i<GOFF>(a), acc);
+        for (int d = 0; d < PPT; ++d) {
+            float v[K];
+#pragma unroll
+            for (int h = 0; h < K / 2; ++h) {
+                uint32_t pk = pa[d][h];
+                asm volatile("" : "+r"(pk));
+                pk += goff2;
+                v[2 * h] = lds(pk & 0xffffu);
+                v[2 * h + 1] = lds(pk >> 16);
             }
-            if (ov[d]) {  // compressive flows / border pile-ups
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < K; ++j) a = fmaf(pw[d][j], v[j], a);
+            acc[d] = a;
+        }
+        // compressive flows / border pile-ups (~3 % of the pairs): the owner walks its elements'
+        // later pairs.  (Measured alternatives at 1080p: a warp-cooperative pass with
+        // red.shared.add.f32 -- a CAS loop on sm_100a that spun ~5 x per call: 1 795 us; the same with
+        // a segmented warp scan and plain read-modify-writes: 1 018 us; this loop not unrolled:
+        // 1 064 us; unrolled by the compiler: 921 us.  An L2 prefetch of the boxes 2..8 channels
+        // ahead (cp.async.bulk.prefetch.tensor) changed nothing: the waits are not DRAM latency.)
+#pragma unroll
+        for (int d = 0; d < PPT; ++d) {
+            if (ov[d]) {
                 uint32_t q = ovf0 + 8u * (ov[d] >> 16);
                 for (uint32_t n = ov[d] & 0xffffu; n > 0; --n, q += 8u) {
                     float w;
                     uint32_t a;
                     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(w), "=r"(a) : "r"(q));
-                    acc = fmaf(w, lds_i<GOFF>(a), acc);
+                    acc[d] = fmaf(w, lds(a + goff), acc[d]);
                 }
             }
-            if ((tapbits >> (8 + d)) & 1u) st_stream1(gi_ptr + (size_t)(d >> 1) * p.W + (d & 1) * 32, acc);
-        });
+        }
+#pragma unroll
+        for (int d = 0; d < PPT; ++d)
+            if ((tapbits >> (8 + d)) & 1u) st_stream1(gi_ptr + (size_t)(d >> 1) * p.W + (d & 1) * 32, acc[d]);
         gi_ptr += plane;
-        __syncthreads();  // stage ST consumed by every thread
+        __syncthreads();  // stage consumed by every thread
         if (tid == 0 && i + NS < nch) issue_loads(i + NS);
-    };
-    for (int i0 = 0; i0 < nch; i0 += NS) {
-        tma::static_for<NS>([&](auto stc) {
-            if (i0 + decltype(stc)::value < nch) channel(stc, i0 + decltype(stc)::value);
-        });
     }
     if (NEED_GFLOW) {
 #pragma unroll

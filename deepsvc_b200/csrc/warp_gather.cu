@@ -398,7 +398,9 @@ extern "C" int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, c
     if (!grad_input && !grad_flow) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (g_bwd_algo < 0) { const char* e = getenv("DSVC_BWD_ALGO"); g_bwd_algo = e ? atoi(e) : 0; }
-    if (grad_input && (g_bwd_algo == 0 || g_bwd_algo == 3)) {
+    // The gather kernel is opt-in (DSVC_WARP_BWD_GATHER): measured on B200 it ties the staged scatter
+    // kernel at 1080p (921 vs 943 us) and loses at 8x64x256x256 (362 vs 280 us) -- DESIGN.md 4.3
+    if (grad_input && g_bwd_algo == 3) {
         WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
         const int r = dsvc_warp_bwd_gather_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p,
                                                   g_bwd_algo == 3, workspace, workspace_bytes, st);

@@ -108,14 +108,15 @@ int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* fl
                       int flow_mode, int layout, void* stream);
 
 /* The same gradient with a caller-provided workspace: NEITHER output needs initialising.
- * With `workspace` (>= dsvc_warp_bwd_workspace_bytes(B,H,W) bytes, any contents; one flag
- * byte per 64 x 16 tile, written before it is read) and an eligible shape (grad_input wanted,
- * C >= 8, W % 4 == 0, W >= 64, H >= 16, 16-byte aligned pointers) grad_input is produced by
- * the destination-owned gather kernel (csrc/warp_bwd_gather.cu: per-tile tap lists in
- * registers, TMA-staged grad_out box, one plain store per element, no atomics) followed by a
- * fix-up launch for the taps outside a tile's search region.  Otherwise grad_input is
- * zero-filled here and dsvc_warp_bwd_f32 runs.  DSVC_WARP_BWD_GATHER (3) forces the gather
- * kernel (cudaErrorInvalidValue if the shape is not eligible). */
+ * By default grad_input is zero-filled here and dsvc_warp_bwd_f32 runs.  With
+ * dsvc_set_warp_bwd_algo(DSVC_WARP_BWD_GATHER), a `workspace` (>= dsvc_warp_bwd_workspace_bytes
+ * (B,H,W) bytes, any contents; one flag byte per 64 x 16 tile, written before it is read) and an
+ * eligible shape (grad_input wanted, W % 4 == 0, 16-byte aligned pointers) grad_input is
+ * produced by the destination-owned gather kernel (csrc/warp_bwd_gather.cu: per-tile tap lists
+ * in registers, TMA-staged grad_out box, one plain store per element, no atomics, no zero-fill)
+ * followed by a fix-up launch for the taps outside a tile's search region; an ineligible shape
+ * is cudaErrorInvalidValue.  The gather kernel is opt-in: measured on B200 it ties the staged
+ * kernel at 1080p and loses at the training shape. */
 int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, const float* flow,
                          float* grad_input, float* grad_flow,
                          int B, int C, int H, int W,

@@ -63,6 +63,7 @@ def timeit(shape, kind, algos=("direct", "staged", "gather"), n=10):
 
 
 if __name__ == "__main__":
+    EXIT = 0
     worst = 0.0
     small = [((1, 8, 32, 64), "smooth"), ((2, 16, 40, 64), "smooth"), ((1, 9, 33, 100), "border"), ((1, 8, 16, 68), "stress")]
     full = small + [((1, 64, 128, 192), k) for k in ("smooth", "stress", "border")] + \
@@ -74,4 +75,35 @@ if __name__ == "__main__":
         timeit((1, 64, 1088, 1920), "smooth")
         timeit((8, 64, 256, 256), "smooth")
         timeit((1, 64, 1088, 1920), "stress", n=3)
-    sys.exit(0 if worst <= 1e-4 else 1)
+    EXIT = 0 if worst <= 1e-4 else 1
+
+
+def time_parts(shape=(1, 64, 1088, 1920), kind="smooth", n=10):
+    """gin-only and gflow-only launches per algorithm (is a two-kernel split worth it?)."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    inp = torch.randn(B, C, H, W, generator=g).to(dev)
+    flow = synthetic.make_flow(kind, B, H, W, g).to(dev)
+    gout = torch.randn(B, C, H, W, generator=g).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for a in ("direct", "staged", "gather"):
+        for gi, gf in ((True, False), (False, True)):
+            ts = []
+            for _ in range(n):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run(a, gout, inp, flow, gi, gf)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            print(f"parts {shape} {a} gin={gi} gflow={gf}: {ts[len(ts) // 2] * 1e3:.1f} us", flush=True)
+
+
+if __name__ == "__main__" and "--parts" in sys.argv:
+    time_parts()
+    time_parts((8, 64, 256, 256))
+
+if __name__ == "__main__":
+    sys.exit(EXIT)
