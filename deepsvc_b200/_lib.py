@@ -10,6 +10,7 @@ from ctypes import c_int, c_int32, c_int64, c_float, c_void_p, c_char_p, c_size_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdeepsvc_b200.so")
+TORCH_LIB_PATH = os.path.join(_HERE, "lib", "libdeepsvc_b200_torch.so")
 
 FLOW_MUL_RECIPROCAL = 0
 FLOW_TRUE_DIVIDE = 1
@@ -88,6 +89,32 @@ def load():
         raise DeepSVCNativeError("deepsvc_b200 ABI version mismatch; rebuild the library")
     _lib = lib
     return lib
+
+
+_ops = None
+_ops_tried = False
+
+
+def torch_ops():
+    """``torch.ops.deepsvc_b200`` -- the TORCH_LIBRARY operator layer (``csrc_torch/ops.cpp``: C++
+    autograd and output allocation over the same C ABI), or None when that library has not
+    been built.  The eager drop-in entry points use it when present (one dispatcher hop per
+    call); without it they go through ctypes.  Either way the arithmetic is the sm_100a kernels
+    of the C-ABI library: set DSVC_NO_TORCH_OPS=1 to force the ctypes path."""
+    global _ops, _ops_tried
+    if _ops_tried:
+        return _ops
+    _ops_tried = True
+    if os.environ.get("DSVC_NO_TORCH_OPS") == "1" or not os.path.isfile(TORCH_LIB_PATH):
+        return None
+    import torch
+    load()                                  # the kernel library first (also checks the ABI version)
+    torch.ops.load_library(TORCH_LIB_PATH)
+    ops = torch.ops.deepsvc_b200
+    if ops.abi_version() != 1:
+        raise DeepSVCNativeError("deepsvc_b200 torch operator library: ABI version mismatch; rebuild")
+    _ops = ops
+    return ops
 
 
 def check(err: int, what: str):

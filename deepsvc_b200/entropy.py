@@ -41,6 +41,8 @@ class _SteRoundFn(torch.autograd.Function):
 def ste_round(x: Tensor) -> Tensor:
     """``compressai.ops.ste_round``: round(x) with identity gradient.  (Value-identical
     to ``round(x) - x.detach() + x``: both subtractions are exact in fp32.)"""
+    if not (x.requires_grad and torch.is_grad_enabled()):
+        return torch.round(x)
     return _SteRoundFn.apply(x)
 
 
@@ -137,6 +139,14 @@ def gc_launch(x, scales, means=None, noise=None, *, want_outputs=False, want_lik
               scale_table=None, scale_bound=0.11, lik_bound=1e-9):
     """One fused GaussianConditional launch (no autograd).  Returns a dict with the
     requested outputs: outputs, likelihood, y_hat, symbols, indexes, bits_partials."""
+    ops = _lib.torch_ops()
+    if ops is not None and not STRICT_STRIDES:
+        want = (1 if want_outputs else 0) | (2 if want_likelihood else 0) | (4 if want_y_hat else 0) | \
+            (8 if want_symbols else 0) | (16 if want_indexes else 0) | (32 if want_bits else 0)
+        o = ops.gc_fwd(x, scales, means, noise, scale_table if want_indexes else None, float(scale_bound),
+                       float(lik_bound), want)
+        return {"outputs": o[0], "likelihood": o[1], "y_hat": o[2], "symbols": o[3], "indexes": o[4],
+                "bits_partials": o[5]}
     x, scales, means, noise = (_in_place_layout(t, "gaussian_conditional") for t in (x, scales, means, noise))
     ins = [t for t in (x, scales, means, noise) if t is not None]
     _require_cuda_f32("gaussian_conditional", *ins)
@@ -471,6 +481,9 @@ class GaussianConditional(EntropyModel):
         if not training:
             noise = None
         sb, lb = self._bounds()
+        ops = _lib.torch_ops()
+        if ops is not None and not STRICT_STRIDES:
+            return ops.gaussian_conditional(inputs, scales, means, noise, sb, lb, want_bits)
         return _GaussianConditionalFn.apply(inputs, scales, means, noise, sb, lb, want_bits)
 
     def likelihood_bits(self, inputs, scales, means=None):
@@ -638,12 +651,13 @@ class EntropyBottleneck(EntropyModel):
         return self.quantiles[:, :, 1:2]
 
     def _param_list(self):
-        ps = [self.quantiles]
+        d = self._parameters   # (looked up per call: swap_entropy_models / load_state_dict may rebind entries)
+        ps = [d["quantiles"]]
         for i in range(5):
-            ps.append(getattr(self, f"_matrix{i}"))
-            ps.append(getattr(self, f"_bias{i}"))
+            ps.append(d[f"_matrix{i}"])
+            ps.append(d[f"_bias{i}"])
             if i < 4:
-                ps.append(getattr(self, f"_factor{i}"))
+                ps.append(d[f"_factor{i}"])
         return ps
 
     def packed_params(self, differentiable: bool) -> Tensor:
@@ -739,9 +753,12 @@ class EntropyBottleneck(EntropyModel):
             noise = n.reshape(self.channels, x.size(0), -1).transpose(0, 1).reshape(x.shape).contiguous()
         if not training:
             noise = None
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._parameters.values())
         packed = self.packed_params(need_grad)
         lb = float(np.float32(self._lik_bound))
+        ops = _lib.torch_ops()
+        if ops is not None:
+            return ops.entropy_bottleneck(x, packed, noise, lb, want_bits)
         return _EntropyBottleneckFn.apply(x.contiguous() if not x.is_contiguous() else x,
                                           packed, noise, lb, want_bits)
 

@@ -252,6 +252,10 @@ class _WarpFn(torch.autograd.Function):
 
 def torch_warp(tensorInput: torch.Tensor, tensorFlow: torch.Tensor) -> torch.Tensor:
     """Backward bilinear warp, border clamp, align_corners=True (``modules.py:25-62``)."""
+    ops = _lib.torch_ops()
+    if ops is not None and _algo == _lib.WARP_AUTO and not STRICT_STRIDES:
+        # one dispatcher hop: checks, output allocation and autograd live in csrc_torch/ops.cpp
+        return ops.torch_warp(tensorInput, tensorFlow, _flow_mode)
     if torch.is_grad_enabled() and (tensorInput.requires_grad or tensorFlow.requires_grad):
         _check(tensorInput, tensorFlow)
         return _WarpFn.apply(tensorInput, tensorFlow)

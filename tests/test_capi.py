@@ -68,3 +68,17 @@ def test_state_dict_names_match_reference_checkpoints(oracle):
     import deepsvc_b200 as d
     assert sorted(d.GaussianConditional(None).state_dict()) == sorted(oracle.GaussianConditional(None).state_dict())
     assert sorted(d.EntropyBottleneck(6).state_dict()) == sorted(oracle.EntropyBottleneck(6).state_dict())
+
+
+def test_torch_operator_library_loads_and_registers_ops():
+    """libdeepsvc_b200_torch.so (csrc_torch/ops.cpp) loads without a GPU and registers the
+    deepsvc_b200:: operators with the dispatcher (no compute calls here)."""
+    import torch
+    from deepsvc_b200 import _lib
+    ops = _lib.torch_ops()
+    assert ops is not None, "build() compiles deepsvc_b200/lib/libdeepsvc_b200_torch.so"
+    assert ops.abi_version() == 1
+    for name in ("warp_fwd", "warp_bwd", "torch_warp", "gc_fwd", "gaussian_conditional", "eb_fwd",
+                 "entropy_bottleneck"):
+        assert hasattr(torch.ops.deepsvc_b200, name)
+        assert getattr(torch.ops.deepsvc_b200, name).default._schema is not None

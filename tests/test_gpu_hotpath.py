@@ -197,3 +197,56 @@ def test_codec_path_bitstreams_match_oracle(oracle):
         rv = torch.from_numpy(dec.decode_stream_array(idx, tables)).reshape(ss.shape).to(dev)
         y_hat = gc.dequantize(rv, ms)
         assert torch.equal(y_hat.cpu(), oracle.ste_round(yo - mo) + mo)
+
+
+def test_torch_ops_layer_matches_ctypes_path(oracle):
+    """The TORCH_LIBRARY operator layer (csrc_torch/ops.cpp) and the ctypes binding launch the same
+    kernels: identical outputs and gradients, and the ops are visible to the dispatcher."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import _lib, synthetic
+    from deepsvc_b200.entropy import _EntropyBottleneckFn, _GaussianConditionalFn
+    from deepsvc_b200.warp import _WarpFn
+    ops = _lib.torch_ops()
+    assert ops is not None, "libdeepsvc_b200_torch.so not built (build() compiles it)"
+    assert "deepsvc_b200::torch_warp" in str(torch.ops.deepsvc_b200.torch_warp.default._schema)
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    inp = torch.randn(2, 16, 64, 96, generator=g).to(dev)
+    flow = synthetic.smooth_flow(2, 64, 96, g).to(dev)
+    cot = torch.randn(2, 16, 64, 96, generator=g).to(dev)
+    res = []
+    for fn in (lambda a, b: ops.torch_warp(a, b, _lib.FLOW_MUL_RECIPROCAL), _WarpFn.apply):
+        a, b = inp.clone().requires_grad_(True), flow.clone().requires_grad_(True)
+        out = fn(a, b)
+        out.backward(cot)
+        res.append((out.detach(), a.grad, b.grad))
+    assert torch.equal(res[0][0], res[1][0])
+    for x, y in zip(res[0][1:], res[1][1:]):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-6)      # atomics order only
+    # GaussianConditional, noise mode, all three inputs differentiable, batch-strided slices
+    y, s, m = synthetic.make_latents(3, 16, 6, 10, g)
+    nz = (torch.rand(3, 16, 6, 10, generator=g) - 0.5).to(dev)
+    res = []
+    for fn in (ops.gaussian_conditional, _GaussianConditionalFn.apply):
+        yy, ss, mm = (t.to(dev).clone().requires_grad_(True) for t in (y, s, m))
+        ys, sl, ms, ns = (t.chunk(2, 1)[1] for t in (yy, ss, mm, nz))
+        out, lik, yhat, bits = fn(ys, sl, ms, ns, 0.11, 1e-9, True)
+        (torch.log(lik).sum() + (out * 0.3).sum() + yhat.sum()).backward()
+        res.append((out.detach(), lik.detach(), yhat.detach(), bits, yy.grad, ss.grad, mm.grad))
+    for x, y_ in zip(res[0], res[1]):
+        assert torch.equal(x, y_)
+    # EntropyBottleneck, round mode, gradient to the packed parameters and z
+    eb = d.EntropyBottleneck(8).to(dev)
+    z = (torch.randn(2, 8, 5, 7, generator=g) * 3).to(dev)
+    res = []
+    for fn in (ops.entropy_bottleneck, _EntropyBottleneckFn.apply):
+        zz = z.clone().requires_grad_(True)
+        packed = eb.packed_params(True)
+        out, lik, zhat, bits = fn(zz, packed, None, 1e-9, True)
+        (torch.log(lik).sum() + zhat.sum() + out.sum()).backward()
+        grads = [p.grad.clone() for p in eb.parameters()]
+        for p in eb.parameters():
+            p.grad = None
+        res.append([out.detach(), lik.detach(), zhat.detach(), bits, zz.grad] + grads)
+    for x, y_ in zip(res[0], res[1]):
+        assert torch.allclose(x, y_, rtol=1e-5, atol=1e-7)
