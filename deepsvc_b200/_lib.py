@@ -62,6 +62,8 @@ SIGNATURES = {
     "dsvc_rans_decoder_create": (c_void_p, [_P, c_int64]),
     "dsvc_rans_decoder_destroy": (None, [_P]),
     "dsvc_rans_decoder_decode": (c_int, [_P, _P, c_int64, _P, c_int, c_int, _P, _P, _P]),
+    "dsvc_rans_encode_many": (c_int, [_P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int]),
+    "dsvc_rans_decode_many": (c_int, [_P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int]),
 }
 
 _lib = None

@@ -124,6 +124,71 @@ class RansDecoder:
         return self.decode_stream(indexes, cdfs, cdfs_sizes, offsets)
 
 
+def _ptr_array(arrs):
+    return (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def _table_arrays(tables):
+    n = len(tables)
+    return (_ptr_array([t.cdfs for t in tables]), (ctypes.c_int32 * n)(*[t.n for t in tables]),
+            (ctypes.c_int32 * n)(*[t.stride for t in tables]), _ptr_array([t.sizes for t in tables]),
+            _ptr_array([t.offsets for t in tables]))
+
+
+def encode_many(jobs, threads: int = 0):
+    """Encode independent streams in parallel on host threads (``dsvc_rans_encode_many``).
+    jobs: [(symbols int32 array, indexes int32 array, CdfTables), ...]; stream k is
+    byte-identical to ``BufferedRansEncoder().encode_with_indexes(*jobs[k]); flush()``.
+    Returns a list of ``bytes``."""
+    import os
+    lib = _lib.load()
+    n = len(jobs)
+    if n == 0:
+        return []
+    syms = [_i32(j[0]) for j in jobs]
+    idxs = [_i32(j[1]) for j in jobs]
+    tabs = [j[2] for j in jobs]
+    for s, i in zip(syms, idxs):
+        if s.size != i.size:
+            raise ValueError("symbols and indexes differ in length")
+    counts = (ctypes.c_int64 * n)(*[s.size for s in syms])
+    cdfs, n_cdfs, strides, sizes, offs = _table_arrays(tabs)
+    extra = 0
+    while True:
+        caps = [(s.size * (2 + 4 * extra) + 1024) * 4 for s in syms]   # 32 bits per symbol is ample for real streams
+        outs = [np.empty(c, dtype=np.uint8) for c in caps]
+        out_len = (ctypes.c_int64 * n)()
+        err = lib.dsvc_rans_encode_many(_ptr_array(syms), _ptr_array(idxs), counts, n, cdfs, n_cdfs, strides, sizes,
+                                        offs, _ptr_array(outs), (ctypes.c_int64 * n)(*caps), out_len,
+                                        int(threads) or min(n, os.cpu_count() or 1))
+        if err == 0:
+            return [o[:l].tobytes() for o, l in zip(outs, out_len)]
+        if extra >= 2:
+            raise ValueError("rans encoder: index or symbol table out of range")
+        extra += 1                      # (or every symbol bypass-coded: retry with room for 11 words each)
+
+
+def decode_many(jobs, threads: int = 0):
+    """Decode independent streams in parallel (``dsvc_rans_decode_many``).
+    jobs: [(stream bytes, indexes int32 array, CdfTables), ...] -> list of int32 numpy arrays."""
+    import os
+    lib = _lib.load()
+    n = len(jobs)
+    if n == 0:
+        return []
+    bufs = [np.frombuffer(j[0], dtype=np.uint8) for j in jobs]
+    idxs = [_i32(j[1]) for j in jobs]
+    tabs = [j[2] for j in jobs]
+    outs = [np.empty(i.size, dtype=np.int32) for i in idxs]
+    cdfs, n_cdfs, strides, sizes, offs = _table_arrays(tabs)
+    err = lib.dsvc_rans_decode_many(_ptr_array(bufs), (ctypes.c_int64 * n)(*[b.size for b in bufs]), _ptr_array(idxs),
+                                    (ctypes.c_int64 * n)(*[i.size for i in idxs]), n, cdfs, n_cdfs, strides, sizes, offs,
+                                    _ptr_array(outs), int(threads) or min(n, os.cpu_count() or 1))
+    if err:
+        raise ValueError("rans decoder: corrupt stream or tables out of range")
+    return outs
+
+
 def pmf_to_quantized_cdf(pmf, precision: int = 16):
     """``compressai._CXX.pmf_to_quantized_cdf`` (list of float -> list of int)."""
     p = np.ascontiguousarray(np.asarray(pmf, dtype=np.float32).reshape(-1))
@@ -134,4 +199,5 @@ def pmf_to_quantized_cdf(pmf, precision: int = 16):
     return out.tolist()
 
 
-__all__ = ["BufferedRansEncoder", "RansEncoder", "RansDecoder", "CdfTables", "pmf_to_quantized_cdf"]
+__all__ = ["BufferedRansEncoder", "RansEncoder", "RansDecoder", "CdfTables", "pmf_to_quantized_cdf",
+           "encode_many", "decode_many"]

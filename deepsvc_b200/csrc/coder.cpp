@@ -12,9 +12,12 @@
 // What is different from the reference pipeline: symbols and table indexes arrive as
 // flat int32 buffers copied once from the device (pinned), not as Python lists built
 // with .tolist() per slice (image_model.py:241-242).
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/deepsvc_b200.h"
@@ -35,11 +38,18 @@ struct Encoder {
     std::vector<Sym> syms;
 };
 
+constexpr int kLutBits = 8;  // symbol search starts from a 256-entry table per CDF
+
 struct Decoder {
     std::vector<uint32_t> words;
     size_t pos = 0;
     uint64_t x = 0;
     bool ok = false;
+    // lut[ci << kLutBits | b] = the symbol whose interval contains the cumulative value
+    // b << (16 - kLutBits); rebuilt when the tables change
+    std::vector<uint16_t> lut;
+    const int32_t* lut_cdfs = nullptr;
+    int lut_n = 0, lut_stride = 0;
 };
 
 struct Tables {
@@ -202,6 +212,21 @@ int dsvc_rans_decoder_decode(void* h, const int32_t* indexes, int64_t n, const i
     if (!d.ok) return DSVC_ERR_INVALID_ARG;
     const uint32_t mask = (1u << kPrecision) - 1;
     bool err = false;
+    if (d.lut_cdfs != cdfs || d.lut_n != n_cdfs || d.lut_stride != cdf_stride) {
+        d.lut.assign((size_t)n_cdfs << kLutBits, 0);
+        for (int ci = 0; ci < n_cdfs; ++ci) {
+            const int32_t* cdf = cdfs + (size_t)ci * cdf_stride;
+            const int32_t size = cdf_sizes[ci];
+            if (size < 2 || size > cdf_stride) return DSVC_ERR_INVALID_ARG;
+            int sidx = 0;
+            for (int b = 0; b < (1 << kLutBits); ++b) {
+                const uint32_t cum = (uint32_t)b << (kPrecision - kLutBits);
+                while (sidx + 2 < size && (uint32_t)cdf[sidx + 1] <= cum) ++sidx;
+                d.lut[((size_t)ci << kLutBits) | b] = (uint16_t)sidx;
+            }
+        }
+        d.lut_cdfs = cdfs; d.lut_n = n_cdfs; d.lut_stride = cdf_stride;
+    }
     for (int64_t i = 0; i < n; ++i) {
         const int32_t ci = indexes[i];
         if (ci < 0 || ci >= n_cdfs) return DSVC_ERR_INVALID_ARG;
@@ -209,14 +234,11 @@ int dsvc_rans_decoder_decode(void* h, const int32_t* indexes, int64_t n, const i
         const int32_t size = cdf_sizes[ci];
         const int32_t max_value = size - 2;
         const uint32_t cum = (uint32_t)(d.x & mask);
-        // first entry > cum (the table is strictly increasing): binary search
-        int lo = 0, hi = size;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((uint32_t)cdf[mid] > cum) hi = mid; else lo = mid + 1;
-        }
-        const int32_t s = lo - 1;
-        if (s < 0 || s + 1 >= size) return DSVC_ERR_INVALID_ARG;
+        // the symbol whose interval [cdf[s], cdf[s+1]) contains cum (the table is strictly
+        // increasing): start from the 256-entry table, walk up (a step or two for peaked pmfs)
+        int32_t s = d.lut[((size_t)ci << kLutBits) | (cum >> (kPrecision - kLutBits))];
+        while (s + 2 < size && (uint32_t)cdf[s + 1] <= cum) ++s;
+        if (s < 0 || s + 1 >= size || (uint32_t)cdf[s] > cum || (uint32_t)cdf[s + 1] <= cum) return DSVC_ERR_INVALID_ARG;
         const uint32_t start = (uint32_t)cdf[s], freq = (uint32_t)(cdf[s + 1] - cdf[s]);
         uint64_t x = d.x;
         x = freq * (x >> kPrecision) + (x & mask) - start;
@@ -245,6 +267,132 @@ int dsvc_rans_decoder_decode(void* h, const int32_t* indexes, int64_t n, const i
         out[i] = value + offsets[ci];
     }
     return 0;
+}
+
+
+}  // extern "C"
+
+/* ---- many independent streams at once (one stream = one BufferedRansEncoder's worth: e.g. the y
+ * symbols of all 8 slices of one codec of one frame).  A single rANS stream is sequential by
+ * construction (one 64-bit state, symbols in reverse), so the parallelism of a byte-compatible
+ * coder is ACROSS streams: mv / res, y / z, and the frames in flight.  Streams are handed to
+ * `n_threads` host threads through an atomic cursor. */
+
+namespace {
+
+// One stream, encoded straight from the symbol / index arrays in reverse (no intermediate
+// symbol vector): emitted words are collected and laid out as [state lo, state hi, words
+// in reverse emission order] -- the bytes of dsvc_rans_encoder_push + _flush.
+int encode_stream(const int32_t* symbols, const int32_t* indexes, int64_t n, const Tables& t,
+                  std::vector<uint32_t>& words, uint8_t* out, int64_t out_cap, int64_t* out_len) {
+    words.clear();
+    words.reserve((size_t)n / 2 + 16);
+    uint64_t x = kRansL;
+    auto put = [&](uint32_t start, uint32_t freq) {
+        const uint64_t x_max = ((kRansL >> kPrecision) << 32) * freq;
+        if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
+        x = ((x / freq) << kPrecision) + (x % freq) + start;
+    };
+    auto put_bits = [&](uint32_t val) {
+        const uint32_t freq = 1u << (16 - kBypassPrecision);
+        const uint64_t x_max = ((kRansL >> 16) << 32) * freq;
+        if (x >= x_max) { words.push_back((uint32_t)x); x >>= 32; }
+        x = (x << kBypassPrecision) | val;
+    };
+    for (int64_t i = n - 1; i >= 0; --i) {
+        const int32_t ci = indexes[i];
+        if (ci < 0 || ci >= t.n_cdfs) return DSVC_ERR_INVALID_ARG;
+        const int32_t* cdf = t.cdfs + (size_t)ci * t.stride;
+        const int32_t max_value = t.sizes[ci] - 2;
+        if (max_value < 0 || max_value + 1 >= t.stride + 1) return DSVC_ERR_INVALID_ARG;
+        int32_t value = symbols[i] - t.offsets[ci];
+        uint32_t raw = 0;
+        if (value < 0) {
+            raw = (uint32_t)(-2 * (int64_t)value - 1);
+            value = max_value;
+        } else if (value >= max_value) {
+            raw = (uint32_t)(2 * ((int64_t)value - max_value));
+            value = max_value;
+        }
+        if (value == max_value) {
+            // pushed order: main, count digits (15, 15, ..., rest), raw chunks 0..n-1 -> reversed here
+            int32_t n_bypass = 0;
+            while (n_bypass < 8 && (raw >> (n_bypass * kBypassPrecision)) != 0) ++n_bypass;
+            for (int32_t j = n_bypass - 1; j >= 0; --j) put_bits((raw >> (j * kBypassPrecision)) & kMaxBypassVal);
+            int32_t val = n_bypass, n15 = 0;
+            while (val >= (int32_t)kMaxBypassVal) { ++n15; val -= kMaxBypassVal; }
+            put_bits((uint32_t)val);
+            for (int32_t j = 0; j < n15; ++j) put_bits(kMaxBypassVal);
+        }
+        put((uint32_t)cdf[value], (uint32_t)(cdf[value + 1] - cdf[value]));
+    }
+    const int64_t nbytes = (int64_t)(words.size() + 2) * 4;
+    if (nbytes > out_cap) return DSVC_ERR_INVALID_ARG;
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    std::memcpy(out, &lo, 4);
+    std::memcpy(out + 4, &hi, 4);
+    for (size_t k = 0; k < words.size(); ++k) std::memcpy(out + 8 + 4 * k, &words[words.size() - 1 - k], 4);
+    *out_len = nbytes;
+    return 0;
+}
+
+template <class F>
+int run_streams(int n_streams, int n_threads, F&& one) {
+    if (n_streams <= 0) return 0;
+    n_threads = std::max(1, std::min(n_threads, n_streams));
+    std::atomic<int> next{0}, err{0};
+    auto worker = [&]() {
+        for (;;) {
+            const int s = next.fetch_add(1);
+            if (s >= n_streams) break;
+            const int e = one(s);
+            if (e) err.store(e);
+        }
+    };
+    if (n_threads == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_threads; ++k) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    return err.load();
+}
+
+}  // namespace
+
+extern "C" {
+
+int dsvc_rans_encode_many(const int32_t* const* symbols, const int32_t* const* indexes, const int64_t* counts,
+                          int n_streams, const int32_t* const* cdfs, const int32_t* n_cdfs,
+                          const int32_t* cdf_strides, const int32_t* const* cdf_sizes,
+                          const int32_t* const* offsets, uint8_t* const* out, const int64_t* out_cap,
+                          int64_t* out_len, int n_threads) {
+    if (n_streams < 0 || (n_streams > 0 && (!symbols || !indexes || !counts || !cdfs || !n_cdfs || !cdf_strides ||
+                                            !cdf_sizes || !offsets || !out || !out_cap || !out_len)))
+        return DSVC_ERR_INVALID_ARG;
+    return run_streams(n_streams, n_threads, [&](int s) -> int {
+        if (counts[s] < 0 || (counts[s] > 0 && (!symbols[s] || !indexes[s])) || !out[s]) return DSVC_ERR_INVALID_ARG;
+        thread_local std::vector<uint32_t> words;
+        const Tables t{cdfs[s], n_cdfs[s], cdf_strides[s], cdf_sizes[s], offsets[s]};
+        return encode_stream(symbols[s], indexes[s], counts[s], t, words, out[s], out_cap[s], &out_len[s]);
+    });
+}
+
+int dsvc_rans_decode_many(const uint8_t* const* streams, const int64_t* stream_len, const int32_t* const* indexes,
+                          const int64_t* counts, int n_streams, const int32_t* const* cdfs, const int32_t* n_cdfs,
+                          const int32_t* cdf_strides, const int32_t* const* cdf_sizes,
+                          const int32_t* const* offsets, int32_t* const* out, int n_threads) {
+    if (n_streams < 0 || (n_streams > 0 && (!streams || !stream_len || !indexes || !counts || !cdfs || !n_cdfs ||
+                                            !cdf_strides || !cdf_sizes || !offsets || !out)))
+        return DSVC_ERR_INVALID_ARG;
+    return run_streams(n_streams, n_threads, [&](int s) -> int {
+        void* h = dsvc_rans_decoder_create(streams[s], stream_len[s]);
+        const int e = dsvc_rans_decoder_decode(h, indexes[s], counts[s], cdfs[s], n_cdfs[s], cdf_strides[s],
+                                               cdf_sizes[s], offsets[s], out[s]);
+        dsvc_rans_decoder_destroy(h);
+        return e;
+    });
 }
 
 }  // extern "C"

@@ -268,6 +268,27 @@ int dsvc_rans_decoder_decode(void* dec, const int32_t* indexes, int64_t n, const
                              int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
                              const int32_t* offsets, int32_t* out_symbols);
 
+/* Many independent streams coded in parallel on `n_threads` host threads (stream s is what
+ * one BufferedRansEncoder / RansDecoder would produce / consume: byte-identical).  A single
+ * rANS stream is sequential; the parallelism of a byte-compatible coder is across streams --
+ * mv / res codecs, y / z, and the frames in flight (image_model.py:217-221,253-254 once per
+ * codec and frame).  All arrays have n_streams entries; tables are per stream.  out[s] must
+ * hold (counts[s] * 3 + 2) * 4 bytes in the worst case (every symbol bypass-coded); out_len[s]
+ * receives the stream length. */
+int dsvc_rans_encode_many(const int32_t* const* symbols, const int32_t* const* indexes,
+                          const int64_t* counts, int n_streams,
+                          const int32_t* const* cdfs, const int32_t* n_cdfs,
+                          const int32_t* cdf_strides, const int32_t* const* cdf_sizes,
+                          const int32_t* const* offsets,
+                          uint8_t* const* out, const int64_t* out_cap, int64_t* out_len,
+                          int n_threads);
+int dsvc_rans_decode_many(const uint8_t* const* streams, const int64_t* stream_len,
+                          const int32_t* const* indexes, const int64_t* counts, int n_streams,
+                          const int32_t* const* cdfs, const int32_t* n_cdfs,
+                          const int32_t* cdf_strides, const int32_t* const* cdf_sizes,
+                          const int32_t* const* offsets,
+                          int32_t* const* out, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

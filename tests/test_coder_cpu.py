@@ -113,3 +113,85 @@ def test_patch_reference_rebinds_names(reference_modules):
     finally:
         d.unpatch_reference()
     assert modules.torch_warp is orig
+
+
+def _rans64_reference(syms, scale_bits=16):
+    """rANS with a 64-bit state and 32-bit renormalisation, written out from the published
+    recurrences (Duda 2013; F. Giesen's rans64.h, public domain) on Python ints -- independent of
+    csrc/coder.cpp and of the oracle's coder: x starts at L = 2^31; symbols are encoded LAST to
+    FIRST; encoding (start, freq) first emits the low 32 bits of x while
+    x >= ((L >> scale_bits) << 32) * freq, then x <- (x // freq << scale_bits) + x % freq + start;
+    the final x follows as two words; the word emitted last comes first in the stream."""
+    L = 1 << 31
+    x, words = L, []
+    for start, freq, bits in reversed(syms):
+        if x >= ((L >> bits) << 32) * freq:
+            words.append(x & 0xFFFFFFFF)
+            x >>= 32
+        x = ((x // freq) << bits) + (x % freq) + start
+    out = [x & 0xFFFFFFFF, x >> 32] + words[::-1]
+    return b"".join(int(w).to_bytes(4, "little") for w in out)
+
+
+def test_rans64_known_answer_stream():
+    """Known-answer test of the wire format: a hand-checkable stream, and a longer one against the
+    big-int recurrences above.  Both the C++ coder and the oracle's pure-Python coder must
+    reproduce the bytes; compressai's bypass convention (4-bit chunks, count first) is spelled out."""
+    from compressai import ans as oans
+    from deepsvc_b200 import ans
+    # one CDF over 4 symbols with offset 0: freqs 8192, 16384, 32768 and the escape 8192 (2^16 total)
+    cdf = [[0, 8192, 24576, 57344, 65536]]
+    lens, offs = [5], [0]
+    t = ans.CdfTables(cdf, lens, offs)
+    # (1) the single symbol 1: x = ((2^31 // 16384) << 16) + 2^31 % 16384 + 8192 = 2^33 + 8192
+    #     = 0x2_0000_2000 -> words [0x00002000, 0x00000002], no renormalisation word
+    want = bytes.fromhex("00200000" "02000000")
+    assert _rans64_reference([(8192, 16384, 16)]) == want
+    assert ans.encode_many([([1], [0], t)], 1) == [want]
+    e = ans.BufferedRansEncoder()
+    e.encode_with_indexes([1], [0], t)
+    assert e.flush() == want
+    o = oans.BufferedRansEncoder()
+    o.encode_with_indexes([1], [0], cdf, lens, offs)
+    assert o.flush() == want
+    # (2) a longer message incl. out-of-range values.  Symbol value v with max_value = 3 (the last
+    # table entry is the escape): v < 0 -> raw = -2 v - 1, v >= 3 -> raw = 2 (v - 3); the escape is
+    # followed by the number n of non-zero 4-bit chunks of raw (as digits 15, 15, ..., rest, each a
+    # uniform 4-bit symbol) and then the n chunks, least significant first.
+    rng = np.random.default_rng(7)
+    msg = rng.integers(0, 3, size=400).tolist() + [3, 7, -1, -40, 100000, 0, 2]
+    syms = []
+    for v in msg:
+        raw = 0
+        if v < 0:
+            raw, v = -2 * v - 1, 3
+        elif v >= 3:
+            raw, v = 2 * (v - 3), 3
+        syms.append((cdf[0][v], cdf[0][v + 1] - cdf[0][v], 16))
+        if v == 3:
+            n = 0
+            while (raw >> (4 * n)) != 0:
+                n += 1
+            val = n
+            while val >= 15:
+                syms.append((15, 1, 4))
+                val -= 15
+            syms.append((val, 1, 4))
+            for j in range(n):
+                syms.append(((raw >> (4 * j)) & 15, 1, 4))
+    want = _rans64_reference(syms)
+    idx = [0] * len(msg)
+    assert ans.encode_many([(msg, idx, t)], 1) == [want]
+    e = ans.BufferedRansEncoder()
+    e.encode_with_indexes(msg, idx, t)
+    assert e.flush() == want
+    o = oans.BufferedRansEncoder()
+    o.encode_with_indexes(msg, idx, cdf, lens, offs)
+    assert o.flush() == want
+    assert ans.decode_many([(want, idx, t)], 1)[0].tolist() == msg
+    d = ans.RansDecoder()
+    d.set_stream(want)
+    assert d.decode_stream(idx, t) == msg
+    # streams are independent of how many threads code them
+    jobs = [(msg, idx, t)] * 5
+    assert ans.encode_many(jobs, 4) == [want] * 5

@@ -152,26 +152,30 @@ def test_codec_path_bitstreams_match_oracle(oracle):
     from compressai import ans as oans
     dev = torch.device("cuda:0")
     C, h, w = 16, 10, 14
+    # tables are evaluated on the module's device on both sides (CPU and CUDA erfc / sigmoid differ in
+    # the last bit, and compressai builds them where the parameters live): the oracle runs on the GPU
     eb_o, gc_o = oracle.make_entropy_models(C, seed=11)
+    eb_o, gc_o = eb_o.to(dev), gc_o.to(dev)
     eb_o.update(force=True)
+    gc_o.update_scale_table(oracle.get_scale_table(), force=True)
     eb = dsvc.EntropyBottleneck(C)
-    eb.load_state_dict({k: v for k, v in eb_o.state_dict().items()
+    eb.load_state_dict({k: v.cpu() for k, v in eb_o.state_dict().items()
                         if k not in ("_offset", "_quantized_cdf", "_cdf_length")}, strict=False)
     eb = eb.to(dev).eval()
     eb.update(force=True)
     gc = dsvc.GaussianConditional(None).to(dev).eval()
     gc.update_scale_table(oracle.get_scale_table())
-    assert torch.equal(gc.quantized_cdf.cpu(), gc_o.quantized_cdf)
-    assert torch.equal(eb.quantized_cdf.cpu(), eb_o.quantized_cdf)
+    assert torch.equal(gc.quantized_cdf.cpu(), gc_o.quantized_cdf.cpu())
+    assert torch.equal(eb.quantized_cdf.cpu(), eb_o.quantized_cdf.cpu())
 
     g = torch.Generator().manual_seed(3)
     z = torch.randn(1, C, 3, 4, generator=g) * 4
     z[0, 0, 0, 0] = 200.0   # outside the table -> bypass coding
-    z_str_o = eb_o.compress(z)
+    z_str_o = eb_o.compress(z.to(dev))
     z_str = eb.compress(z.to(dev))
     assert z_str == z_str_o
     z_hat = eb.decompress(z_str, z.shape[-2:])
-    assert torch.equal(z_hat.cpu(), eb_o.decompress(z_str_o, z.shape[-2:]))
+    assert torch.equal(z_hat.cpu(), eb_o.decompress(z_str_o, z.shape[-2:]).cpu())
 
     y, s, m = synthetic.make_latents(1, C, h, w, g)
     y[0, 1, 2, 3] = m[0, 1, 2, 3] + 3000.0   # bypass
@@ -181,8 +185,8 @@ def test_codec_path_bitstreams_match_oracle(oracle):
     tables = gc._cdf_tables()
     for ys, ss, ms, yo, so, mo in zip(yd.chunk(4, 1), sd.chunk(4, 1), md.chunk(4, 1),
                                       y.chunk(4, 1), s.chunk(4, 1), m.chunk(4, 1)):
-        idx_o = gc_o.build_indexes(so)
-        sym_o = gc_o.quantize(yo, "symbols", mo)
+        idx_o = gc_o.build_indexes(so.to(dev)).cpu()
+        sym_o = gc_o.quantize(yo.to(dev), "symbols", mo.to(dev)).cpu()
         enc_o.encode_with_indexes(sym_o.reshape(-1).tolist(), idx_o.reshape(-1).tolist(),
                                   gc_o.quantized_cdf.tolist(), gc_o.cdf_length.tolist(), gc_o.offset.tolist())
         sym, idx, y_hat = gc.quantize_and_index(ys, ss, ms)
@@ -250,3 +254,52 @@ def test_torch_ops_layer_matches_ctypes_path(oracle):
         res.append([out.detach(), lik.detach(), zhat.detach(), bits, zz.grad] + grads)
     for x, y_ in zip(res[0], res[1]):
         assert torch.allclose(x, y_, rtol=1e-5, atol=1e-7)
+
+
+def test_frame_symbol_pipeline_streams_and_roundtrip(oracle):
+    """8f-1: FrameSymbolPipeline (18 launches into one device buffer, one pinned copy, four streams
+    coded by dsvc_rans_encode_many) produces exactly the bytes of the per-slice drop-in path
+    (quantize_and_index + BufferedRansEncoder, EntropyBottleneck.compress) and decodes back to the
+    encoder's y_hat / z_hat bit for bit."""
+    import deepsvc_b200 as dsvc
+    from deepsvc_b200 import ans, synthetic
+    from deepsvc_b200.codec import FrameSymbolDecoder, FrameSymbolPipeline
+    dev = torch.device("cuda:0")
+    cpu_in = synthetic.make_pframe_inputs(B=1, H=128, W=192, seed=5)
+    cpu_in["mv_y"][0, 3, 2, 1] = cpu_in["mv_means"][0, 3, 2, 1] + 4000.0      # bypass-coded symbols
+    cpu_in["res_z"][0, 5, 0, 1] = -300.0
+    d = synthetic.to_device(cpu_in, dev)
+    models = {}
+    for name, ch in (("mv", 64), ("res", 96)):
+        eb_o, _ = oracle.make_entropy_models(ch, seed=ch)
+        eb = dsvc.EntropyBottleneck(ch)
+        eb.load_state_dict(eb_o.state_dict(), strict=False)
+        eb = eb.to(dev).eval()
+        eb.update(force=True)
+        gc = dsvc.GaussianConditional(None).to(dev).eval()
+        gc.update_scale_table(synthetic.get_scale_table())
+        models[name] = (eb, gc)
+    pipe = FrameSymbolPipeline(d, models, depth=2)
+    for slot in (0, 1, 0):                         # slot reuse waits for the previous copy
+        pipe.launch(slot, d)
+    jobs = pipe.jobs(0)
+    streams = ans.encode_many(jobs, threads=3)
+    assert streams == ans.encode_many(pipe.jobs(1), threads=1)
+    k = 0
+    for name in ("mv", "res"):
+        eb, gc = models[name]
+        enc = ans.BufferedRansEncoder()
+        for y_s, s_s, m_s in zip(d[f"{name}_y"].chunk(8, 1), d[f"{name}_scales"].chunk(8, 1), d[f"{name}_means"].chunk(8, 1)):
+            sym, idx, _ = gc.quantize_and_index(y_s, s_s, m_s)
+            enc.encode_with_indexes(sym, idx, gc._cdf_tables())
+        assert streams[k] == enc.flush(), f"{name} y stream"
+        assert [streams[k + 1]] == eb.compress(d[f"{name}_z"]), f"{name} z stream"
+        k += 2
+    dec = FrameSymbolDecoder(pipe, d)
+    got = dec.decode(streams, [(j[1], j[2]) for j in jobs], threads=2)
+    y_ref, z_ref = pipe.reconstruction(0)
+    for name in ("mv", "res"):
+        assert torch.equal(got[name][0], y_ref[name]) and torch.equal(got[name][1], z_ref[name])
+        assert torch.equal(y_ref[name], torch.round(d[f"{name}_y"] - d[f"{name}_means"]) + d[f"{name}_means"])
+        assert torch.equal(got[name][1], models[name][0].decompress([streams[2 * ("mv", "res").index(name) + 1]],
+                                                                    d[f"{name}_z"].shape[-2:]))
