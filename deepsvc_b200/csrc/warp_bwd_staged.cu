@@ -560,17 +560,23 @@ int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const flo
     // 1 range 280 us, 2 ranges 314 us, 4 ranges 337 us although 512 tiles are only 1.7 waves
     const int slots = 2 * sms_of[dev];
     int csplit = 1;
+#ifdef DSVC_TUNE
     static int env_split = -1;
     if (env_split < 0) { const char* e = getenv("DSVC_BWD_CSPLIT"); env_split = e ? atoi(e) : 0; }
     if (env_split > 0) csplit = env_split;
-    else while (ntiles * csplit < (long long)slots && p.C / (csplit * 2) >= 16) csplit *= 2;
+    else
+#endif
+    while (ntiles * csplit < (long long)slots && p.C / (csplit * 2) >= 16) csplit *= 2;
     const int cper = (p.C + csplit - 1) / csplit;
     if (gflow && csplit > 1) {
         const cudaError_t e = cudaMemsetAsync(gflow, 0, (size_t)p.B * 2 * p.H * p.W * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
-    static int perm_mul = 0;
-    if (perm_mul == 0) { const char* e = getenv("DSVC_BWD_PERM"); perm_mul = e ? (atoi(e) | 1) : 1; }
+    static int perm_mul = 1;  // lane -> share permutation multiplier (odd values measured: no effect)
+#ifdef DSVC_TUNE
+    static bool perm_read = false;
+    if (!perm_read) { const char* e = getenv("DSVC_BWD_PERM"); perm_mul = e ? (atoi(e) | 1) : 1; perm_read = true; }
+#endif
     const unsigned grid = (unsigned)(ntiles * csplit);
     if (gin)
         warp_bwd_staged_kernel<true><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(

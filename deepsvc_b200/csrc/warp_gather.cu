@@ -340,7 +340,7 @@ extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
     return sizeof(WarpSched) + 48;  // scheduler state of the persistent staged kernel
 }
 
-static int g_bwd_algo = -1;  // DSVC_WARP_BWD_* (tests / profiling; default from $DSVC_BWD_ALGO)
+static int g_bwd_algo = 0;  // DSVC_WARP_BWD_* (dsvc_set_warp_bwd_algo: tests / profiling)
 extern "C" int dsvc_set_warp_bwd_algo(int algo) {
     DSVC_CHECK_ARG(algo >= 0 && algo <= 3);
     g_bwd_algo = algo;
@@ -359,7 +359,6 @@ extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, cons
     cudaStream_t st = (cudaStream_t)stream;
     WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
     // 0 = auto (staged kernel when the shape is eligible), 1 = per-pixel kernel, 2 = staged forced
-    if (g_bwd_algo < 0) { const char* e = getenv("DSVC_BWD_ALGO"); g_bwd_algo = e ? atoi(e) : 0; }
     const int algo = g_bwd_algo == 3 ? 0 : g_bwd_algo;
     if (algo != 1) {
         const int r = dsvc_warp_bwd_staged_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p,
@@ -397,7 +396,6 @@ extern "C" int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, c
     DSVC_CHECK_ARG(layout == DSVC_LAYOUT_NCHW);
     if (!grad_input && !grad_flow) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g_bwd_algo < 0) { const char* e = getenv("DSVC_BWD_ALGO"); g_bwd_algo = e ? atoi(e) : 0; }
     // The gather kernel is opt-in (DSVC_WARP_BWD_GATHER): measured on B200 it ties the staged scatter
     // kernel at 1080p (921 vs 943 us) and loses at 8x64x256x256 (362 vs 280 us) -- DESIGN.md 4.3
     if (grad_input && g_bwd_algo == 3) {

@@ -594,6 +594,10 @@ static int launch_persist(const float* input, const float* flow, float* out, con
     // per-device set-up (function attributes and SM counts belong to the device, not the process)
     static unsigned long long attr_set = 0;
     static int sms_of[64];
+    // schedule parameters (measured on B200): the last wave's tiles are cut into 2
+    // channel ranges, tiles are ordered row-major inside 20-tile strips.  -DDSVC_TUNE builds read
+    // $DSVC_WARP_TAIL_SPLIT / _TAIL_PCT / _STRIP once per device for re-tuning; the product
+    // library has no environment knobs in its launch path.
     static int env_split = 0, env_tail_pct = 100, env_strip = 20;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
@@ -606,9 +610,11 @@ static int launch_persist(const float* input, const float* flow, float* out, con
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = DSVC_NUM_SMS;
         sms_of[dev] = n;
-        if (const char* e2 = getenv("DSVC_WARP_TAIL_SPLIT")) env_split = atoi(e2);  // tuning knobs
+#ifdef DSVC_TUNE
+        if (const char* e2 = getenv("DSVC_WARP_TAIL_SPLIT")) env_split = atoi(e2);
         if (const char* e2 = getenv("DSVC_WARP_TAIL_PCT")) env_tail_pct = atoi(e2);
         if (const char* e2 = getenv("DSVC_WARP_STRIP")) env_strip = atoi(e2);
+#endif
         attr_set |= 1ull << dev;
     }
     const int num_sms = sms_of[dev];
@@ -674,6 +680,9 @@ int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* o
                                                                       workspace_bytes, st, input2, out2, C2);
     if (!force && (p.C < 8 || p.W < 64 || p.H < 32)) return -1;
     if ((long long)p.B * p.C > (1ll << 30)) return -1;
+#ifdef DSVC_TUNE
+    // tile / box / stage / register-cap variants for re-tuning (DESIGN.md 4.2 lists what was measured);
+    // never compiled into the product library
     static int cfg = -1;
     if (cfg < 0) {
         const char* e = getenv("DSVC_TMA_CFG");  // tuning knob
@@ -706,4 +715,8 @@ int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* o
         case 24: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
         default: return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6, 2, 72>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
     }
+#else
+    // 64 x 16 tiles, 96 x 32 staging box, one channel plane per stage, 6 stages, 2 CTAs per SM, 72 registers
+    return launch_persist<PersistCfg<64, 16, 96, 32, 1, 6, 2, 72>>(input, flow, out, lin_x, lin_y, p, workspace, workspace_bytes, st);
+#endif
 }

@@ -289,8 +289,16 @@ class HostSession:
     SLOTS = 2
 
     def __init__(self, host_inputs: dict, models: dict, device, flow_mode=_lib.FLOW_MUL_RECIPROCAL,
-                 warp_algo=_lib.WARP_AUTO):
+                 warp_algo=_lib.WARP_AUTO, carry_on_device=False):
+        """carry_on_device=False: every input comes from host memory and every output returns to it,
+        each frame.  carry_on_device=True: the codec state the reference itself keeps on the device
+        between frames -- ``ref_frame`` and ``feature`` (``test_video.py:368-369``: the previous
+        frame's reconstruction and its 64-ch feature) -- is uploaded once, and the 64-ch
+        ``warped_feature`` (consumed by the device-side conv transforms, ``modules.py:429-436``)
+        stays on the device; everything else still crosses the host every frame."""
         self.device = device
+        self.carry = ("ref_frame", "feature") if carry_on_device else ()
+        self.keep = ("warped_feature",) if carry_on_device else ()
 
         def pin(t):
             p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -314,7 +322,7 @@ class HostSession:
                                     v if isinstance(v, list) else [v]):
                         d.copy_(h, non_blocking=True)
                 hp.capture()
-            outs = self._flat_outputs(hp)
+            outs = self._flat_outputs(hp, self.keep)
             host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
             self.slots.append({
                 "hp": hp, "dev_in": dev_in, "outs": outs, "host_out": host_out,
@@ -323,16 +331,18 @@ class HostSession:
         torch.cuda.synchronize(device)
         self._pairs = []
         for k, v in self.host_in.items():
+            if k in self.carry:
+                continue            # uploaded once above (device-resident codec state)
             self._pairs += [(k, i) for i in range(len(v))] if isinstance(v, list) else [(k, None)]
-        self.h2d_bytes = sum(t.numel() * t.element_size() for k, v in self.host_in.items()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for k, v in self.host_in.items() if k not in self.carry
                              for t in (v if isinstance(v, list) else [v]))
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in self.slots[0]["outs"])
         self.frame = 0
 
     @staticmethod
-    def _flat_outputs(hp):
+    def _flat_outputs(hp, keep=()):
         o = hp.out
-        return (list(o["spynet"]) + [o["warped_frame"], o["warped_feature"]] +
+        return (list(o["spynet"]) + [o[k] for k in ("warped_frame", "warped_feature") if k not in keep] +
                 list(o["mv_y_hat_slices"]) + [o["mv_z_hat"]] +
                 list(o["res_y_hat_slices"]) + [o["res_z_hat"]] + [hp.bpp])
 

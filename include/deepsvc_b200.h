@@ -148,7 +148,7 @@ int dsvc_blend_f32(const float* weight, const float* warped, const float* pred, 
                    int64_t n, void* stream);
 
 /* Kernel choice of dsvc_warp_bwd_f32 (process-wide; tests and profiling).
- * DSVC_WARP_BWD_AUTO (0, default, or $DSVC_BWD_ALGO): the shared-memory staged kernel
+ * DSVC_WARP_BWD_AUTO (0, default): the shared-memory staged kernel
  * (per-tile transposed-warp CSR, run sums in a shared-memory out-box, row-contiguous RED.ADD.v4.F32
  * into grad_input; csrc/warp_bwd_staged.cu)
  * when C >= 8, W % 4 == 0, W >= 64, H >= 16 and the pointers are 16-byte aligned, else the
