@@ -20,7 +20,7 @@ def main():
     rank, local_rank, world = shard.init_distributed()
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    bound = shard.bind_to_gpu_numa_node(local_rank) if "--numa" in sys.argv else False
+    bound = shard.bind_to_gpu_numa_node(local_rank) if os.environ.get("DSVC_PROBE_NUMA") == "1" else False
     up_b, down_b = 648_034_560, 598_682_896
     h_up = torch.empty(up_b, dtype=torch.uint8, pin_memory=True)
     h_dn = torch.empty(down_b, dtype=torch.uint8, pin_memory=True)
