@@ -38,30 +38,39 @@ warp_fwd_nchw_gather(const float* __restrict__ in, const float* __restrict__ flo
 // thread gather issues ~250 instructions per pixel and is issue-bound at 2.7 TB/s), so this
 // kernel keeps it lean: 32-bit element offsets, taps outside the image read a clamped
 // in-image address with an exactly-zero weight instead of being branched around, a
-// persistent grid strides over 32 x (8*PX) pixel tiles, every thread keeps the 4*C*PX taps of
+// persistent grid works through 32 x (8*PX) pixel tiles, every thread keeps the 4*C*PX taps of
 // its PX pixels in flight at once and loads the NEXT tile's flow before it gathers the
 // current one.  Results are identical to gather_pixel's on finite inputs.
+// Tiles are CLAIMED from a device counter when the caller provides scheduler state (`sched`, the
+// same zero-before / zero-after words as the persistent staged kernel): next to the feature warp
+// only a fraction of this grid's CTAs is resident at once, and a static tile assignment left the
+// late CTAs' tiles to run after it (round 1: the 3-ch warps added their whole time to the frame).
 template <int C, int PX, int FM>
 __global__ void __launch_bounds__(256)
 warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow,
                     float* __restrict__ out, const float* __restrict__ lin_x,
                     const float* __restrict__ lin_y, WarpParams p, unsigned tiles_x,
-                    unsigned tiles_y, unsigned total_tiles) {
+                    unsigned tiles_y, unsigned total_tiles, WarpSched* __restrict__ sched) {
     const unsigned lane = threadIdx.x, wy = threadIdx.y;
     const unsigned W = p.W, H = p.H, plane = H * W;  // C*H*W < 2^31 (checked by the launcher)
     float fx[PX], fy[PX];
-    // tile coordinates advance by gridDim.x tiles per iteration without divisions
-    const unsigned step_r = gridDim.x / tiles_x, step_x = gridDim.x - step_r * tiles_x;
-    const unsigned step_b = step_r / tiles_y, step_y = step_r - step_b * tiles_y;
+    __shared__ unsigned s_claim[2];
     struct Tile { unsigned tx, ty, b; };
-    auto advance = [&](Tile& q) {
-        q.tx += step_x;
-        const unsigned cx = q.tx >= tiles_x ? 1u : 0u;
-        q.tx -= cx ? tiles_x : 0u;
-        q.ty += step_y + cx;
-        const unsigned cy = q.ty >= tiles_y ? 1u : 0u;
-        q.ty -= cy ? tiles_y : 0u;
-        q.b += step_b + cy;
+    auto decode = [&](unsigned t, Tile& q) {
+        const unsigned r = t / tiles_x;
+        q.tx = t - r * tiles_x;
+        q.b = r / tiles_y;
+        q.ty = r - q.b * tiles_y;
+    };
+    unsigned n_claims = 0;
+    // the tile after `t`: the next one off the counter, or the grid stride without scheduler state
+    auto next_tile = [&](unsigned t) -> unsigned {
+        if (!sched) return t + gridDim.x;
+        const unsigned slot = n_claims & 1u;
+        if (lane == 0 && wy == 0) s_claim[slot] = (unsigned)atomicAdd(&sched->next, 1);
+        __syncthreads();  // (two slots: a warp still reading the previous claim is never overwritten)
+        ++n_claims;
+        return s_claim[slot];
     };
     auto load_flow = [&](const Tile& q) {
         const unsigned x = q.tx * 32 + lane, y0 = q.ty * (8 * PX) + wy;
@@ -74,23 +83,19 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
             fy[j] = __ldg(fl + (pix + plane));
         }
     };
-    unsigned t = blockIdx.x;
+    unsigned t = sched ? next_tile(0u) : blockIdx.x;
     Tile next;
-    {
-        const unsigned r = t / tiles_x;
-        next.tx = t - r * tiles_x;
-        next.b = r / tiles_y;
-        next.ty = r - next.b * tiles_y;
-    }
+    decode(t, next);
     if (t < total_tiles) load_flow(next);
-    for (; t < total_tiles; t += gridDim.x) {
+    while (t < total_tiles) {
         const Tile cur = next;
         const unsigned b = cur.b, x = cur.tx * 32 + lane, y0 = cur.ty * (8 * PX) + wy;
         float cfx[PX], cfy[PX];
 #pragma unroll
         for (int j = 0; j < PX; ++j) { cfx[j] = fx[j]; cfy[j] = fy[j]; }
-        advance(next);
-        if (t + gridDim.x < total_tiles) load_flow(next);  // in flight during this tile
+        t = next_tile(t);
+        decode(t, next);
+        if (t < total_tiles) load_flow(next);  // in flight during this tile
         const float* inb = in + (size_t)b * C * plane;
         float* outb = out + (size_t)b * C * plane;
         const float lx = __ldg(lin_x + min(x, W - 1));
@@ -145,6 +150,14 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
                 st_stream1(op, acc);
                 op += plane;
             }
+        }
+    }
+    if (sched && lane == 0 && wy == 0) {
+        // the last CTA to run dry leaves the scheduler state zeroed for the next launch
+        if (atomicAdd(&sched->exited, 1) == (int)gridDim.x - 1) {
+            sched->next = 0;
+            __threadfence();
+            sched->exited = 0;
         }
     }
 }
@@ -282,7 +295,9 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
                 // (no carve-out preference here: this kernel lives on L1 hits -- 26.8 -> 32.8 us at 1080p
                 // with the maximum shared-memory carve-out)
                 const int grid = (int)std::min<long long>(total, slots);
-                kernel<<<grid, dim3(32, 8), 0, st>>>(input, flow, out, lin_x, lin_y, p, tiles_x, tiles_y, (unsigned)total);
+                WarpSched* sched = (workspace && workspace_bytes >= sizeof(WarpSched) && aligned16(workspace))
+                                       ? static_cast<WarpSched*>(workspace) : nullptr;
+                kernel<<<grid, dim3(32, 8), 0, st>>>(input, flow, out, lin_x, lin_y, p, tiles_x, tiles_y, (unsigned)total, sched);
                 return (int)cudaGetLastError();
             };
 #define DSVC_FEWCH(CN) return flow_mode ? launch(warp_fwd_nchw_fewch<CN, PX, 1>) : launch(warp_fwd_nchw_fewch<CN, PX, 0>)

@@ -120,7 +120,7 @@ class PFrameHotPath:
         out = torch.empty_like(inp)
         lin_x, lin_y = _base_grids(inp.device, H, W)
         sx, sy, inv_sx, inv_sy = _scales(H, W)
-        ws = warp_workspace(inp.device, B, H, W, private=True) if C >= 8 else None
+        ws = warp_workspace(inp.device, B, H, W, private=True)   # scheduler words (tile claiming), every warp
         self._keep += [out, lin_x, lin_y, ws]
         self._calls.append((self.lib.dsvc_warp_fwd_f32, (
             inp.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, lin_x.data_ptr(),

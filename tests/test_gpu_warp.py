@@ -460,3 +460,30 @@ def test_two_tensors_one_flow_bit_identical(shape, kind):
     assert int(warp_workspace(_dev(), B, H, W).abs().sum().item()) == 0
     with pytest.raises(RuntimeError):
         warp_forward2(a.requires_grad_(True), b, flow)
+
+
+def test_few_channel_kernel_claims_tiles_and_leaves_scheduler_zeroed(oracle):
+    """The 3-ch kernel claims its tiles from the workspace's scheduler words (so that it can share
+    the SMs with the persistent feature warp): same bits as the static grid-stride order (no
+    workspace), and the words are zero again after every launch."""
+    from deepsvc_b200 import _lib, synthetic
+    from deepsvc_b200.warp import _base_grids, _scales
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(12)
+    for (B, C, H, W) in ((1, 3, 272, 480), (2, 3, 70, 100), (1, 1, 9, 40)):
+        inp = torch.randn(B, C, H, W, generator=g).to(_dev())
+        flow = synthetic.smooth_flow(B, H, W, g).to(_dev())
+        lx, ly = _base_grids(_dev(), H, W)
+        sx, sy, isx, isy = _scales(H, W)
+        ws = torch.zeros(64, dtype=torch.uint8, device=_dev())
+        outs = []
+        for wsp, wsn in ((ws.data_ptr(), ws.numel()), (None, 0), (ws.data_ptr(), ws.numel())):
+            out = torch.empty_like(inp)
+            _lib.check(lib.dsvc_warp_fwd_f32(inp.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, lx.data_ptr(),
+                                             ly.data_ptr(), sx, sy, isx, isy, _lib.FLOW_MUL_RECIPROCAL, _lib.LAYOUT_NCHW,
+                                             _lib.WARP_AUTO, wsp, wsn, torch.cuda.current_stream().cuda_stream), "warp")
+            torch.cuda.synchronize()
+            assert int(ws.view(torch.int32).abs().sum()) == 0
+            outs.append(out)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+        assert_warp_close(outs[0], oracle.torch_warp(inp, flow), "few-channel, claimed tiles")
