@@ -16,6 +16,34 @@
 
 namespace dsvc {
 
+// Programmatic dependent launch (PDL): the forward-path kernels are launched with the
+// programmatic-stream-serialization attribute and begin with pdl_prologue().  A kernel's CTAs may
+// then be scheduled while its predecessor in the stream (or captured graph) is still draining --
+// they block in griddepcontrol.wait until the predecessor has COMPLETED and its writes are visible,
+// so the stream's serial semantics are unchanged; what overlaps is the launch latency and the
+// ramp of the ~20 few-microsecond launches of a frame.  launch_dependents right after the wait lets
+// the successor be scheduled as soon as every CTA of this grid has started.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // The staged warp kernels configure their SMs for the maximum shared-memory carve-out.  A kernel
 // that prefers another L1 / shared-memory split cannot become resident on such an SM until it
 // drains, so the path's short kernels ask for the same carve-out (once per kernel and device)

@@ -85,6 +85,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(kGcThreads) gc_fwd_kernel(GcArgs a) {
     __shared__ float s_tbl[kMaxTable];
     __shared__ double s_red[kGcThreads / 32];
+    pdl_prologue();
     const bool want_idx = a.indexes != nullptr;
     if (want_idx) {
         for (int i = threadIdx.x; i < a.n_table; i += blockDim.x) s_tbl[i] = a.scale_table[i];
@@ -296,6 +297,7 @@ eb_fwd_kernel(const float* __restrict__ z, const float* __restrict__ noise,
               double* __restrict__ bits_partials, float lik_bound, int B, int C, int S) {
     __shared__ float P[kEbP];
     __shared__ double s_red[kEbThreads / 32];
+    pdl_prologue();
     const int c = blockIdx.x;
     for (int i = threadIdx.x; i < kEbP; i += blockDim.x) P[i] = params[(size_t)c * kEbP + i];
     __syncthreads();
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(256)
 bits_finalize_kernel(const double* __restrict__ partials, const int32_t* __restrict__ seg,
                      const double* __restrict__ scales, double* __restrict__ out) {
     __shared__ double s_red[8];
+    pdl_prologue();
     const int i = blockIdx.x;
     const int lo = seg[i], hi = seg[i + 1];
     double acc = 0.0;
@@ -477,8 +480,8 @@ extern "C" int dsvc_gc_fwd_f32(const float* x, const float* scales, const float*
     dim3 grid((unsigned)cdiv(inner, (long long)kGcThreads * kGcVec), (unsigned)rows);
     prefer_max_shared_carveout(gc_fwd_kernel<true>);
     prefer_max_shared_carveout(gc_fwd_kernel<false>);
-    if (vec) gc_fwd_kernel<true><<<grid, kGcThreads, 0, st>>>(a);
-    else gc_fwd_kernel<false><<<grid, kGcThreads, 0, st>>>(a);
+    if (vec) launch_pdl(gc_fwd_kernel<true>, grid, dim3(kGcThreads), 0, st, a);
+    else launch_pdl(gc_fwd_kernel<false>, grid, dim3(kGcThreads), 0, st, a);
     DSVC_RETURN_LAST();
 }
 
@@ -512,8 +515,8 @@ extern "C" int dsvc_eb_fwd_f32(const float* z, const float* noise, const float* 
     DSVC_CHECK_ARG((long long)B * S < (1ll << 31) && cdiv((long long)B * S, kEbThreads) <= 65535);
     dim3 grid((unsigned)C, (unsigned)cdiv((long long)B * S, kEbThreads));
     prefer_max_shared_carveout(eb_fwd_kernel);
-    eb_fwd_kernel<<<grid, kEbThreads, 0, (cudaStream_t)stream>>>(
-        z, noise, params, outputs, likelihood, z_hat, bits_partials, lik_bound, B, C, S);
+    launch_pdl(eb_fwd_kernel, grid, dim3(kEbThreads), 0, (cudaStream_t)stream, z, noise, params, outputs, likelihood,
+               z_hat, bits_partials, lik_bound, B, C, S);
     DSVC_RETURN_LAST();
 }
 
@@ -534,7 +537,7 @@ extern "C" int dsvc_bits_finalize_f64(const double* partials, const int32_t* seg
     DSVC_CHECK_ARG(partials && seg_offsets && scales && out && nseg >= 0);
     if (nseg == 0) return 0;
     prefer_max_shared_carveout(bits_finalize_kernel);
-    bits_finalize_kernel<<<nseg, 256, 0, (cudaStream_t)stream>>>(partials, seg_offsets, scales, out);
+    launch_pdl(bits_finalize_kernel, dim3(nseg), dim3(256), 0, (cudaStream_t)stream, partials, seg_offsets, scales, out);
     DSVC_RETURN_LAST();
 }
 

@@ -55,6 +55,7 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
     const unsigned W = p.W, H = p.H, plane = H * W;  // C*H*W < 2^31 (checked by the launcher)
     float fx[PX], fy[PX];
     __shared__ unsigned s_claim[2];
+    pdl_prologue();
     struct Tile { unsigned tx, ty, b; };
     auto decode = [&](unsigned t, Tile& q) {
         const unsigned r = t / tiles_x;
@@ -297,7 +298,8 @@ extern "C" int dsvc_warp_fwd_f32(const float* input, const float* flow, float* o
                 const int grid = (int)std::min<long long>(total, slots);
                 WarpSched* sched = (workspace && workspace_bytes >= sizeof(WarpSched) && aligned16(workspace))
                                        ? static_cast<WarpSched*>(workspace) : nullptr;
-                kernel<<<grid, dim3(32, 8), 0, st>>>(input, flow, out, lin_x, lin_y, p, tiles_x, tiles_y, (unsigned)total, sched);
+                launch_pdl(kernel, dim3(grid), dim3(32, 8), 0, st, input, flow, out, lin_x, lin_y, p, tiles_x, tiles_y,
+                           (unsigned)total, sched);
                 return (int)cudaGetLastError();
             };
 #define DSVC_FEWCH(CN) return flow_mode ? launch(warp_fwd_nchw_fewch<CN, PX, 1>) : launch(warp_fwd_nchw_fewch<CN, PX, 0>)

@@ -180,6 +180,7 @@ warp_fwd_persist_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
     __shared__ __align__(16) UnitDesc desc[ND];
     __shared__ __align__(16) float2 coords[ND][TW * TH];  // per-pixel source coordinates of a unit
 
+    pdl_prologue();  // (common.cuh: nothing of the predecessor's output is touched before this)
     // (warp index broadcast from lane 0 so that the compiler treats role branches as warp-uniform)
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const size_t plane = (size_t)p.H * p.W;
@@ -647,8 +648,8 @@ static int launch_persist(const float* input, const float* flow, float* out, con
         cudaMemcpyToSymbol(g_trace, &trace, sizeof(trace));
     }
 #endif
-    warp_fwd_persist_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(
-        tm, tm2, input, input2, flow, out, out2, C1, lin_x, lin_y, p, sch, static_cast<WarpSched*>(workspace));
+    launch_pdl(warp_fwd_persist_kernel<Cfg>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm, tm2, input, input2,
+               flow, out, out2, C1, lin_x, lin_y, p, sch, static_cast<WarpSched*>(workspace));
 #ifdef DSVC_TRACE
     if (trace) {
         cudaStreamSynchronize(st);
