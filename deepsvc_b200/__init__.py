@@ -10,7 +10,7 @@ from .warp import (torch_warp, warp_forward, warp_forward2, warp_backward, set_f
                    set_warp_algorithm)
 from .entropy import (EntropyBottleneck, EntropyModel, GaussianConditional, LowerBound, ste_round,
                       bits_finalize, bpp_scale)
-from .fused import mc_blend, spynet_level_warp, warp_with_mse
+from .fused import lrp_add, mc_blend, spynet_level_warp, warp_with_mse
 from .patch import patch_reference, swap_entropy_models, unpatch_reference
 
 __version__ = "0.1.0"
@@ -18,4 +18,4 @@ __version__ = "0.1.0"
 __all__ = ["torch_warp", "warp_forward", "warp_forward2", "warp_backward", "set_flow_arithmetic",
            "set_warp_algorithm", "EntropyBottleneck", "EntropyModel", "GaussianConditional",
            "LowerBound", "ste_round", "bits_finalize", "bpp_scale", "patch_reference",
-           "unpatch_reference", "swap_entropy_models", "spynet_level_warp", "warp_with_mse", "mc_blend"]
+           "unpatch_reference", "swap_entropy_models", "spynet_level_warp", "warp_with_mse", "mc_blend", "lrp_add"]

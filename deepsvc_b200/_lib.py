@@ -41,6 +41,8 @@ SIGNATURES = {
                                     c_float, c_float, c_float, c_float, c_int, _P]),
     "dsvc_warp_fused_slots": (c_int, [c_int, c_int, c_int]),
     "dsvc_blend_f32": (c_int, [_P, _P, _P, _P, c_int64, _P]),
+    "dsvc_lrp_add_f32": (c_int, [_P, _P, _P, c_int64, _P]),
+    "dsvc_lrp_add_bwd_f32": (c_int, [_P, _P, _P, c_int64, _P]),
     "dsvc_set_warp_bwd_algo": (c_int, [c_int]),
     "dsvc_reduce_slots": (c_int, [c_int64, c_int64]),
     "dsvc_gc_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _P,

@@ -172,3 +172,39 @@ extern "C" int dsvc_blend_f32(const float* weight, const float* warped, const fl
         reinterpret_cast<const float4*>(pred), reinterpret_cast<float4*>(out), n4, weight, warped, pred, out, (size_t)n);
     DSVC_RETURN_LAST();
 }
+
+// ------------------------------------------------------------------ LRP add (image_model.py:185-188)
+// `lrp = 0.5 * torch.tanh(lrp); y_hat_slice += lrp`: three eager launches on a [B,Cs,H/16,W/16]
+// tensor per slice (16 slices per frame) -> one.  Same fp32 operations in the same order
+// (tanhf, one multiply, one add): bit-identical.  Differentiable form: d/d y_hat = 1,
+// d/d lrp = 0.5 * (1 - tanh^2), written to grad_lrp when asked for.
+namespace dsvc {
+__global__ void __launch_bounds__(256)
+lrp_add_kernel(const float* __restrict__ y_hat, const float* __restrict__ lrp, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = __fadd_rn(y_hat[i], __fmul_rn(0.5f, tanhf(lrp[i])));
+}
+__global__ void __launch_bounds__(256)
+lrp_add_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ lrp, float* __restrict__ grad_lrp, size_t n) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) {
+        const float t = tanhf(lrp[i]);
+        grad_lrp[i] = grad_out[i] * (0.5f * (1.0f - t * t));
+    }
+}
+}  // namespace dsvc
+
+extern "C" int dsvc_lrp_add_f32(const float* y_hat, const float* lrp, float* out, int64_t n, void* stream) {
+    DSVC_CHECK_ARG(y_hat && lrp && out && n >= 0);
+    if (n == 0) return 0;
+    dsvc::lrp_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(y_hat, lrp, out, (size_t)n);
+    DSVC_RETURN_LAST();
+}
+
+extern "C" int dsvc_lrp_add_bwd_f32(const float* grad_out, const float* lrp, float* grad_lrp, int64_t n, void* stream) {
+    DSVC_CHECK_ARG(grad_out && lrp && grad_lrp && n >= 0);
+    if (n == 0) return 0;
+    dsvc::lrp_add_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad_out, lrp, grad_lrp, (size_t)n);
+    DSVC_RETURN_LAST();
+}
+

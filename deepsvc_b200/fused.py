@@ -95,4 +95,54 @@ def mc_blend(w: torch.Tensor, warped: torch.Tensor, pred: torch.Tensor) -> torch
     return out
 
 
-__all__ = ["spynet_level_warp", "warp_with_mse", "mc_blend"]
+class _LrpAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y_hat, lrp):
+        ctx.save_for_backward(lrp)
+        return _lrp_add_launch(y_hat, lrp, None)
+
+    @staticmethod
+    def backward(ctx, g):
+        (lrp,) = ctx.saved_tensors
+        g_lrp = None
+        if ctx.needs_input_grad[1]:
+            g = g.contiguous()
+            g_lrp = torch.empty_like(lrp)
+            with torch.cuda.device(lrp.device):
+                err = _lib.load().dsvc_lrp_add_bwd_f32(g.data_ptr(), lrp.data_ptr(), g_lrp.data_ptr(), lrp.numel(),
+                                                       _lib.stream_ptr(lrp.device))
+            _lib.check(err, "dsvc_lrp_add_bwd_f32")
+        return (g if ctx.needs_input_grad[0] else None), g_lrp
+
+
+def _lrp_add_launch(y_hat, lrp, out):
+    out = torch.empty_like(y_hat) if out is None else out
+    with torch.cuda.device(y_hat.device):
+        err = _lib.load().dsvc_lrp_add_f32(y_hat.data_ptr(), lrp.data_ptr(), out.data_ptr(), y_hat.numel(),
+                                           _lib.stream_ptr(y_hat.device))
+    _lib.check(err, "dsvc_lrp_add_f32")
+    return out
+
+
+def lrp_add(y_hat: torch.Tensor, lrp: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    """``y_hat + 0.5 * tanh(lrp)`` -- ``image_model.py:185-188`` (``lrp = 0.5 * torch.tanh(lrp);
+    y_hat_slice += lrp``) in one launch instead of three, bit-identical; differentiable in both
+    arguments.  ``inplace=True`` writes into ``y_hat`` like the reference's ``+=`` (no autograd)."""
+    for t in (y_hat, lrp):
+        if not (t.is_cuda and t.dtype == torch.float32):
+            raise RuntimeError("deepsvc_b200.lrp_add: fp32 CUDA tensors required (no CPU fallback)")
+    if y_hat.shape != lrp.shape:
+        raise RuntimeError("deepsvc_b200.lrp_add: shape mismatch")
+    if not (y_hat.is_contiguous() and lrp.is_contiguous()):
+        y_hat_c, lrp = y_hat.contiguous(), lrp.contiguous()
+        if inplace:
+            return y_hat.copy_(_lrp_add_launch(y_hat_c, lrp, None))
+        y_hat = y_hat_c
+    if inplace:
+        return _lrp_add_launch(y_hat, lrp, y_hat)
+    if torch.is_grad_enabled() and (y_hat.requires_grad or lrp.requires_grad):
+        return _LrpAddFn.apply(y_hat, lrp)
+    return _lrp_add_launch(y_hat, lrp, None)
+
+
+__all__ = ["spynet_level_warp", "warp_with_mse", "mc_blend", "lrp_add"]

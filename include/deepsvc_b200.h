@@ -147,6 +147,14 @@ int dsvc_warp_fused_slots(int B, int H, int W);
 int dsvc_blend_f32(const float* weight, const float* warped, const float* pred, float* out,
                    int64_t n, void* stream);
 
+/* out = y_hat + 0.5 * tanh(lrp) over n contiguous floats: the latent-residual-prediction add of
+ * image_model.py:185-188 (`lrp = 0.5 * torch.tanh(lrp); y_hat_slice += lrp`) in one pass instead of
+ * three, bit-identical (same fp32 operations in the same order).  out may alias y_hat (the
+ * reference adds in place).  dsvc_lrp_add_bwd_f32: grad_lrp = grad_out * 0.5 * (1 - tanh(lrp)^2)
+ * (the gradient with respect to y_hat is grad_out itself). */
+int dsvc_lrp_add_f32(const float* y_hat, const float* lrp, float* out, int64_t n, void* stream);
+int dsvc_lrp_add_bwd_f32(const float* grad_out, const float* lrp, float* grad_lrp, int64_t n, void* stream);
+
 /* Kernel choice of dsvc_warp_bwd_f32 (process-wide; tests and profiling).
  * DSVC_WARP_BWD_AUTO (0, default): the shared-memory staged kernel
  * (per-tile transposed-warp CSR, run sums in a shared-memory out-box, row-contiguous RED.ADD.v4.F32

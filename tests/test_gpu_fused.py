@@ -79,3 +79,27 @@ def test_mc_blend_bit_identical(shape):
     wv, av, bv = (t.reshape(-1)[1:].contiguous()[1:] for t in (w, a, b))
     wv, av, bv = (t.reshape(-1)[1:] for t in (w, a, b))
     assert torch.equal(d.mc_blend(wv, av, bv), wv * av + (1 - wv) * bv)
+
+
+def test_lrp_add_bit_identical_and_gradients():
+    """image_model.py:185-188 (`lrp = 0.5 * torch.tanh(lrp); y_hat_slice += lrp`) in one launch."""
+    import deepsvc_b200 as d
+    g = torch.Generator().manual_seed(8)
+    dev = torch.device("cuda:0")
+    for shape in ((1, 8, 68, 120), (8, 12, 16, 16), (1, 3, 5, 7)):
+        y = (torch.randn(shape, generator=g) * 3).to(dev)
+        l = (torch.randn(shape, generator=g) * 2).to(dev)
+        want = y + 0.5 * torch.tanh(l)
+        assert torch.equal(d.lrp_add(y, l), want)
+        y2 = y.clone()
+        assert d.lrp_add(y2, l, inplace=True) is y2 and torch.equal(y2, want)
+        # a batch-strided slice (y.chunk(8, 1)[i] with B > 1) is copied once
+        big = (torch.randn(shape[0], shape[1] * 2, *shape[2:], generator=g)).to(dev)
+        ys = big.chunk(2, 1)[1]
+        assert torch.equal(d.lrp_add(ys, l), ys + 0.5 * torch.tanh(l))
+        ya, la = y.clone().requires_grad_(True), l.clone().requires_grad_(True)
+        yb, lb = y.clone().requires_grad_(True), l.clone().requires_grad_(True)
+        cot = torch.randn(shape, generator=g).to(dev)
+        d.lrp_add(ya, la).backward(cot)
+        (yb + 0.5 * torch.tanh(lb)).backward(cot)
+        assert torch.equal(ya.grad, yb.grad) and torch.allclose(la.grad, lb.grad, rtol=1e-5, atol=1e-7)

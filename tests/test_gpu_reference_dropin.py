@@ -296,3 +296,29 @@ def test_pframe_hotpath_vs_gpu_oracle_1080p(oracle):
         assert torch.equal(got[f"{name}_z_hat"], want[f"{name}_z_hat"])
         assert _rel(got[f"bpp_{name}"], want[f"bpp_{name}"]) <= 1e-4
     assert _rel(got["bpp"], want["bpp"]) <= 1e-4
+
+
+def test_iframe_codec_and_any_compressai_model_through_the_dropins(reference_modules):
+    """the I-frame codec ``ICIP2020ResB`` (``image_model.py:440-488``: M = 320 in 10
+    slices of 32 channels, N = 192) uses the same entropy ops; ``swap_entropy_models`` wires any
+    model built on them.  Unmodified reference class, stock vs patched on the GPU: bit-identical."""
+    import deepsvc_b200 as d
+    modules, image_model, video_model = reference_modules
+    torch.manual_seed(5)
+    net = image_model.ICIP2020ResB().to(_dev()).eval()
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(1, 3, 256, 448, generator=g).to(_dev())
+    with torch.no_grad():
+        stock = net(x)
+    try:
+        d.patch_reference(modules, video_model, image_model)
+        assert d.swap_entropy_models(net) == 2
+        with torch.no_grad():
+            patched = net(x)
+    finally:
+        d.unpatch_reference()
+    assert torch.equal(patched["x_hat"], stock["x_hat"])
+    for k in ("y", "z"):
+        a, b = patched["likelihoods"][k], stock["likelihoods"][k]
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-12)
+        assert _rel(torch.log(a.double()).sum().item(), torch.log(b.double()).sum().item()) <= 1e-4
