@@ -54,16 +54,70 @@ def test_warp_with_mse(oracle, shape, kind):
     assert float(d.warp_with_mse(ref, flow, cur)[1]) == float(l)  # fixed-order sum
 
 
-def test_fused_ops_refuse_training_and_cpu():
+def test_fused_ops_refuse_cpu_and_wide_tensors():
     import deepsvc_b200 as d
     x = torch.rand(1, 3, 8, 8)
     with pytest.raises(RuntimeError):
         d.spynet_level_warp(x, torch.zeros(1, 2, 4, 4))
-    xg = x.to(_dev())
-    with pytest.raises(RuntimeError):
-        d.spynet_level_warp(xg, torch.zeros(1, 2, 4, 4, device=_dev(), requires_grad=True))
     with pytest.raises(RuntimeError):
         d.spynet_level_warp(torch.rand(1, 8, 8, 8, device=_dev()), torch.zeros(1, 2, 4, 4, device=_dev()))
+
+
+def test_fusions_are_differentiable_like_the_unfused_chains(oracle):
+    """Gradients of spynet_level_warp (modules.py:163-168), warp_with_mse (video_model.py:37-38) and
+    mc_blend (modules.py:436) against autograd of the reference's own statements on the GPU."""
+    import deepsvc_b200 as d
+    import torch.nn.functional as F
+    dev = _dev()
+    g = torch.Generator().manual_seed(21)
+
+    def close(a, b, what):
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{what}: {err}"
+
+    # SpyNet level: flow_up feeds the warp AND is used downstream (flow = flow_up + conv(...))
+    im = torch.rand(2, 3, 48, 80, generator=g).to(dev)
+    fl = (torch.randn(2, 2, 24, 40, generator=g) * 2).to(dev)
+    c_up, c_w = torch.randn(2, 2, 48, 80, generator=g).to(dev), torch.randn(2, 3, 48, 80, generator=g).to(dev)
+    res = []
+    for fused in (False, True):
+        a, b = im.clone().requires_grad_(True), fl.clone().requires_grad_(True)
+        if fused:
+            up, w = d.spynet_level_warp(a, b)
+        else:
+            up = F.interpolate(b, (48, 80), mode="bilinear", align_corners=False) * 2.0
+            w = oracle.torch_warp(a, up)
+        ((up * c_up).sum() + (w * c_w).sum()).backward()
+        res.append((a.grad, b.grad))
+    close(res[1][0], res[0][0], "spynet grad_im2")
+    close(res[1][1], res[0][1], "spynet grad_flow")
+    # warp + warp_loss
+    ref = torch.rand(1, 3, 64, 96, generator=g).to(dev)
+    cur = torch.rand(1, 3, 64, 96, generator=g).to(dev)
+    mv = (torch.randn(1, 2, 64, 96, generator=g) * 3).to(dev)
+    cot = torch.randn(1, 3, 64, 96, generator=g).to(dev)
+    res = []
+    for fused in (False, True):
+        a, b, c = (t.clone().requires_grad_(True) for t in (ref, mv, cur))
+        if fused:
+            w, loss = d.warp_with_mse(a, b, c)
+        else:
+            w = oracle.torch_warp(a, b)
+            loss = torch.mean((w - c).pow(2))
+        (loss * 1000.0 + (w * cot).sum()).backward()
+        res.append((a.grad, b.grad, c.grad))
+    for x, y, nm in zip(res[1], res[0], ("grad_ref", "grad_flow", "grad_cur")):
+        close(x, y, "warp_with_mse " + nm)
+    # blend
+    ws, wa, pr = (torch.rand(1, 3, 40, 56, generator=g).to(dev) for _ in range(3))
+    res = []
+    for fused in (False, True):
+        a, b, c = (t.clone().requires_grad_(True) for t in (ws, wa, pr))
+        out = d.mc_blend(a, b, c) if fused else a * b + (1 - a) * c
+        (out * cot[:, :, :40, :56]).sum().backward()
+        res.append((a.grad, b.grad, c.grad))
+    for x, y in zip(res[1], res[0]):
+        close(x, y, "mc_blend")
 
 
 @pytest.mark.parametrize("shape", [(1, 3, 64, 96), (2, 3, 33, 47), (1, 3, 1088, 1920), (1, 1, 1, 3)])
