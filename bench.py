@@ -416,7 +416,7 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(prof) and (Hh, Ww, B) == (1088, 1920, 1) and args.flow == "smooth":
         try:
-            t = json.load(open(prof))
+            t = json.load(open(prof))["fused" if args.fuse_frame_warp else "separate"]
             roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
             roofline["traffic_source"] = t["source"]
         except Exception:
