@@ -303,3 +303,40 @@ def test_frame_symbol_pipeline_streams_and_roundtrip(oracle):
         assert torch.equal(y_ref[name], torch.round(d[f"{name}_y"] - d[f"{name}_means"]) + d[f"{name}_means"])
         assert torch.equal(got[name][1], models[name][0].decompress([streams[2 * ("mv", "res").index(name) + 1]],
                                                                     d[f"{name}_z"].shape[-2:]))
+
+
+@pytest.mark.parametrize("carry", [False, True])
+def test_host_session_delivers_the_frame_to_host_memory(oracle, carry):
+    """HostSession.process (the host-buffer entry point timed as `e2e`): pinned host inputs -> H2D ->
+    graph -> D2H; what arrives in host memory equals the device-resident PFrameHotPath results, over
+    several pipelined frames and both slots; with carry_on_device the reference's device-resident
+    state (ref_frame / feature, test_video.py:368-369) is uploaded once and warped_feature stays."""
+    import deepsvc_b200 as d
+    from deepsvc_b200 import synthetic
+    from deepsvc_b200.hotpath import HostSession, PFrameHotPath
+    dev = torch.device("cuda:0")
+    cpu_in = synthetic.make_pframe_inputs(B=1, H=128, W=192, seed=9)
+    models = {}
+    for name, ch in (("mv", 64), ("res", 96)):
+        eb_o, _ = oracle.make_entropy_models(ch, seed=ch)
+        eb = d.EntropyBottleneck(ch)
+        eb.load_state_dict(eb_o.state_dict(), strict=False)
+        models[name] = (eb.to(dev).eval(), d.GaussianConditional(None).to(dev).eval())
+    hp = PFrameHotPath(synthetic.to_device(cpu_in, dev), models)
+    hp.run()
+    torch.cuda.synchronize()
+    want = HostSession._flat_outputs(hp, ("warped_feature",) if carry else ())
+    sess = HostSession(cpu_in, models, dev, carry_on_device=carry)
+    full_in = sum(t.numel() * 4 for k, v in cpu_in.items() for t in (v if isinstance(v, list) else [v]))
+    carried = (cpu_in["ref_frame"].numel() + cpu_in["feature"].numel()) * 4
+    assert sess.h2d_bytes == full_in - (carried if carry else 0)
+    slots = [sess.process() for _ in range(5)]
+    assert slots == [0, 1, 0, 1, 0]
+    sess.drain()
+    for slot in (0, 1):
+        got = sess.wait(slot)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b.cpu())
+    b0, b1 = sess.host_bpp(0)
+    assert abs(b0 + b1 - hp.results()["bpp"]) < 1e-12
