@@ -666,7 +666,9 @@ class EntropyBottleneck(EntropyModel):
         if differentiable:
             return pack_bottleneck_params(self)
         ps = self._param_list()
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        # in-place updates (optimizer steps, load_state_dict) bump the version counters; a move of the
+        # module (.to / .cuda) replaces every parameter's storage, the first one's included
+        key = (ps[0].data_ptr(),) + tuple(p._version for p in ps)
         if self._packed_cache is None or self._packed_cache[0] != key:
             with torch.no_grad():
                 self._packed_cache = (key, pack_bottleneck_params(self))
