@@ -69,7 +69,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--flow", default="smooth", choices=["smooth", "stress", "border"])
+    ap.add_argument("--flow", default="smooth", choices=["smooth", "stress", "border", "gentle"],
+                    help="smooth (default, SURVEY 8d primary), stress, border; gentle = a low-gradient flow for one secondary line")
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tma"])
     ap.add_argument("--branches4", action="store_true",
                     help="capture the 4-branch DAG (feature | 3-ch warps | mv | res entropy) instead "

@@ -34,6 +34,13 @@ def smooth_flow(B, H, W, gen, sigma=4.0, jitter=0.25, scale=1.0):
     return (flow * scale).contiguous()
 
 
+def gentle_flow(B, H, W, gen):
+    """A low-gradient flow (N(0, 1) px nodes on the 1/16 grid = +-0.09 px/px, +-0.05 px jitter):
+    not a SURVEY 8d family, used by one secondary bench line to show how much of the feature
+    warp's shared-memory bank conflicts comes from the primary flow's +-0.35 px/px gradient."""
+    return smooth_flow(B, H, W, gen, sigma=1.0, jitter=0.05)
+
+
 def stress_flow(B, H, W, gen, sigma=16.0):
     return (torch.randn(B, 2, H, W, generator=gen) * sigma).contiguous()
 
@@ -56,6 +63,8 @@ def make_flow(kind, B, H, W, gen):
         return stress_flow(B, H, W, gen)
     if kind == "border":
         return border_flow(B, H, W, gen, margin=max(1, min(H, W) // 4), reach=40.0)
+    if kind == "gentle":
+        return gentle_flow(B, H, W, gen)
     raise ValueError(f"unknown flow kind {kind!r}")
 
 
@@ -79,7 +88,7 @@ def make_pframe_inputs(B=1, H=256, W=448, seed=SEED, flow_kind="smooth", trainin
     """All tensors one P-frame's hot path consumes, on the CPU."""
     assert H % 64 == 0 and W % 64 == 0, "the reference pads frames to multiples of 64"
     gen = torch.Generator().manual_seed(seed)
-    mk = {"smooth": smooth_flow, "stress": stress_flow, "border": border_flow}[flow_kind]
+    mk = {"smooth": smooth_flow, "stress": stress_flow, "border": border_flow, "gentle": gentle_flow}[flow_kind]
     d = {}
     d["pyr_img"], d["pyr_flow"] = [], []
     for k in range(4):
