@@ -102,7 +102,8 @@ class FrameSymbolPipeline:
         """Enqueue one frame's 18 symbol launches on the current stream and its single
         device-to-host copy on the copy stream.  Asynchronous."""
         s = self.slots[slot_index]
-        key = id(inputs)
+        # the launcher arguments are bound once per set of input tensors (keyed on their addresses)
+        key = tuple(inputs[f"{n}_{k}"].data_ptr() for n in CODECS for k in ("y", "scales", "means", "z"))
         if s["calls"] is None or s["calls"][0] != key:
             s["calls"] = (key, self._bind(s, inputs))
         st = torch.cuda.current_stream(self.device)
