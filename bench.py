@@ -207,10 +207,13 @@ def crop_rows(inputs, frac_rows):
 
 
 def time_cpu_path(cpu_inputs, models_o, steps, warmup, threads, budget_s):
-    """Times oracle.pframe_hotpath on the host. Returns (frames/s, description, n_steps)."""
+    """Times oracle.pframe_hotpath on the host. Returns (frames/s, description, n_steps).
+    `cpu_inputs`: one input set, or a list of sets used in rotation (the `config.l2` policy)."""
     import torch
     from oracle import reference_ops as R
     torch.set_num_threads(threads)
+    sets = cpu_inputs if isinstance(cpu_inputs, list) else [cpu_inputs]
+    cpu_inputs = sets[0]
     Hh = cpu_inputs["ref_frame"].shape[2]
     with torch.no_grad():
         t0 = time.perf_counter()
@@ -223,19 +226,32 @@ def time_cpu_path(cpu_inputs, models_o, steps, warmup, threads, budget_s):
     if est_full * total > budget_s:
         rows = int(budget_s / (est_full * total) * Hh) // 64 * 64
         rows = min(max(rows, 64), Hh)
-    sample = crop_rows(cpu_inputs, rows) if rows < Hh else cpu_inputs
+    samples = [crop_rows(ci, rows) if rows < Hh else ci for ci in sets]
     frac = rows / Hh
     with torch.no_grad():
-        for _ in range(warmup):
-            R.pframe_hotpath(sample, models_o)
+        for i in range(warmup):
+            R.pframe_hotpath(samples[i % len(samples)], models_o)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            R.pframe_hotpath(sample, models_o)
+        for i in range(steps):
+            R.pframe_hotpath(samples[i % len(samples)], models_o)
         dt = time.perf_counter() - t0
     fps = steps * frac / dt
     desc = (f"{steps} steps (+{warmup} warm-up) of the top {rows}/{Hh} rows of every tensor of one "
             f"{cpu_inputs['ref_frame'].shape[3]}x{Hh} P-frame (value scaled by {frac:.4f}), torch {threads} threads, {dt:.1f}s")
     return fps, desc, dt / steps
+
+
+def l2_note(total_bytes, nsets):
+    """How the timed region keeps its reads out of L2 (part of `config`: a property of the workload)."""
+    if nsets == 1:
+        return (f"inputs larger than L2: {total_bytes / 1e6:.0f} MB working set per frame vs 126 MB L2, "
+                "no flush needed")
+    return (f"{nsets} distinct input/output sets replayed in rotation ({nsets} x {total_bytes / 1e6:.0f} MB "
+            "> 126 MB L2): every replay reads its frame from HBM")
+
+
+def default_sets(total_bytes):
+    return 8 if total_bytes < (256 << 20) else 1
 
 
 def frame_size(args):
@@ -255,7 +271,8 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     Hh, Ww = frame_size(args)
     metric, workload, _ = labels(Hh, Ww, args.flow)
-    cpu_in = synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16, flow_kind=args.flow)
+    nsets = args.sets or default_sets(synthetic.pframe_algorithmic_bytes(B, Hh, Ww)["total"])
+    cpu_in = [synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16 + 100 * i, flow_kind=args.flow) for i in range(nsets)]
     models = build_models("cpu")
     models_o = oracle_models(models)
     fps, desc, s_per_step = time_cpu_path(cpu_in, models_o, args.steps, max(args.warmup, 1) if args.steps > 3 else 1,
@@ -264,7 +281,9 @@ def run_reference(args):
         "impl": "reference", "metric": metric, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload, "flow": args.flow},
+        "data": "synthetic",
+        "config": {"workload": workload, "flow": args.flow,
+                   "l2": l2_note(synthetic.pframe_algorithmic_bytes(B, Hh, Ww)["total"], nsets)},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -331,7 +350,7 @@ def run_ours(args):
     bytes_alg = synthetic.pframe_algorithmic_bytes(B, Hh, Ww)
     # L2: 126 MB.  A frame whose working set fits is run over `nsets` distinct input/output sets
     # in rotation so that every replay finds its data in HBM, not in L2
-    nsets = args.sets or (8 if bytes_alg["total"] < (256 << 20) else 1)
+    nsets = args.sets or default_sets(bytes_alg["total"])
 
     models = build_models(dev)
     cpu_sets = [synthetic.make_pframe_inputs(B=B, H=Hh, W=Ww, seed=16 + rank + 100 * i, flow_kind=args.flow)
@@ -512,12 +531,11 @@ def run_ours(args):
             "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "flow": args.flow, "warp_algo": args.algo,
+            # `config` holds what defines the workload (identical in the --impl reference line); how this
+            # arm ran it is under `run`
+            "config": {"workload": workload, "flow": args.flow, "l2": l2_note(bytes_alg["total"], nsets)},
+            "run": {"warp_algo": args.algo,
                        "per_gpu": "each rank codes its own independent sequence (no data-path collective)",
-                       "l2": (f"inputs larger than L2: {bytes_alg['total'] / 1e6:.0f} MB working set per frame vs 126 MB L2, no flush needed"
-                              if nsets == 1 else
-                              f"{nsets} distinct input/output sets replayed in rotation ({nsets} x {bytes_alg['total'] / 1e6:.0f} MB "
-                              "> 126 MB L2): every replay reads its frame from HBM"),
                        "timed_region": f"{len(blocks)} blocks of {args.steps} steps (>= {MIN_TIMED_S} s in total); "
                                        "value = steps / median block time, max over ranks",
                        "launch": (f"CUDA graph replay of the frame's {hp.n_launches} hot-path launches, "
