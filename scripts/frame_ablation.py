@@ -16,8 +16,11 @@ gpu_in = synthetic.to_device(cpu_in, dev)
 models = bench.build_models(dev)
 
 
+FUSE = "--fuse" in sys.argv
+
+
 def timed(keep, label):
-    hp = PFrameHotPath(gpu_in, models)
+    hp = PFrameHotPath(gpu_in, models, fuse_frame_warp=FUSE)
     hp._calls = [c for c in hp._calls if keep(c[2]) or c[2] == "bits_finalize"]
     hp.capture()
     for _ in range(20):
@@ -43,3 +46,5 @@ timed(lambda n: feat(n) or ent(n), "feature + 18 entropy launches")
 timed(lambda n: full3(n) or pyr(n), "five 3-ch warps only")
 timed(ent, "18 entropy launches only")
 timed(lambda n: True, "whole frame")
+timed(lambda n: feat(n) or (full3(n) and True) or ent(n), "feature + full-res 3-ch + entropy")
+timed(lambda n: feat(n) or pyr(n), "feature + the three small pyramid warps")
