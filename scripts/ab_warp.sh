@@ -1,4 +1,7 @@
 #!/bin/bash
+# NOTE (round 2): the DSVC_TMA_CFG / DSVC_WARP_* knobs exist only in a tuning build:
+#   DSVC_TUNE=1 python -c "import __graft_entry__ as g; g.build(force=True)"
+# (the product library compiles one configuration and reads no environment variables).
 # A/B of the staged warp kernel's tuning knobs at 1080p C=64 (run under gpurun).
 out=gpurun_out/ab_warp.txt; : > $out
 run() { echo "== $* $EXTRA" >> $out; env "$@" python scripts/prof_kernels.py --what feature --iters 40 $EXTRA 2>&1 | grep "warp_fwd" >> $out; }
