@@ -51,6 +51,8 @@ SIGNATURES = {
     "dsvc_gc_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float,
                                 c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P]),
     "dsvc_eb_reduce_slots": (c_int, [c_int, c_int, c_int]),
+    "dsvc_eb_pack_f32": (c_int, [_P, _P, c_int, _P]),
+    "dsvc_eb_pack_bwd_f32": (c_int, [_P, _P, _P, c_int, _P]),
     "dsvc_eb_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
     "dsvc_eb_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_int, c_int, c_int, _P]),
     "dsvc_bits_finalize_f64": (c_int, [_P, _P, _P, _P, c_int, _P]),

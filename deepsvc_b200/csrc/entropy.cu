@@ -541,6 +541,120 @@ extern "C" int dsvc_bits_finalize_f64(const double* partials, const int32_t* seg
     DSVC_RETURN_LAST();
 }
 
+// ------------------------------------------------------------------ bottleneck parameter packing
+// [C, 60] packed parameters from the module's 15 raw tensors in ONE launch (forward) and their
+// gradients in one more (backward): softplus of the matrices, the biases, tanh of the factors,
+// the median (quantiles[:, 0, 1]), one pad.  The eager version is ~15 tiny launches forward and
+// ~25 backward per bottleneck -- most of the kernel nodes of a training step.  Same math functions
+// as ATen (softplus: x > 20 ? x : log1p(exp(x)); tanhf).
+namespace dsvc {
+struct EbRaw {
+    const float* matrix[5];   // [C, f_{i+1}, f_i]
+    const float* bias[5];     // [C, f_{i+1}, 1]
+    const float* factor[4];   // [C, f_{i+1}, 1]
+    const float* quantiles;   // [C, 1, 3]
+};
+struct EbRawGrad {
+    float* matrix[5];
+    float* bias[5];
+    float* factor[4];
+    float* quantiles;
+};
+// packed offsets: layer i occupies [off_i, off_i + m_i + b_i + f_i)
+__device__ __forceinline__ void eb_slot(int j, int& layer, int& kind, int& k, int& width) {
+    // widths: matrices 3, 9, 9, 9, 3; biases 3, 3, 3, 3, 1; factors 3, 3, 3, 3
+    const int msz[5] = {3, 9, 9, 9, 3}, bsz[5] = {3, 3, 3, 3, 1};
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        if (j < off + msz[i]) { layer = i; kind = 0; k = j - off; width = msz[i]; return; }
+        off += msz[i];
+        if (j < off + bsz[i]) { layer = i; kind = 1; k = j - off; width = bsz[i]; return; }
+        off += bsz[i];
+        if (i < 4) {
+            if (j < off + 3) { layer = i; kind = 2; k = j - off; width = 3; return; }
+            off += 3;
+        }
+    }
+    layer = 0; kind = j == 58 ? 3 : 4; k = 0; width = 1;  // 58: median, 59: pad
+}
+
+__global__ void __launch_bounds__(64) eb_pack_kernel(EbRaw r, float* __restrict__ packed, int C) {
+    const int c = blockIdx.x, j = threadIdx.x;
+    if (c >= C || j >= kEbP) return;
+    int layer, kind, k, width;
+    eb_slot(j, layer, kind, k, width);
+    float v = 0.0f;
+    if (kind == 0) {
+        const float x = r.matrix[layer][(size_t)c * width + k];
+        v = x > 20.0f ? x : log1pf(expf(x));
+    } else if (kind == 1) {
+        v = r.bias[layer][(size_t)c * width + k];
+    } else if (kind == 2) {
+        v = tanhf(r.factor[layer][(size_t)c * width + k]);
+    } else if (kind == 3) {
+        v = r.quantiles[(size_t)c * 3 + 1];
+    }
+    packed[(size_t)c * kEbP + j] = v;
+}
+
+__global__ void __launch_bounds__(64)
+eb_pack_bwd_kernel(EbRaw r, const float* __restrict__ g_packed, EbRawGrad g, int C) {
+    const int c = blockIdx.x, j = threadIdx.x;
+    if (c >= C || j >= kEbP) return;
+    int layer, kind, k, width;
+    eb_slot(j, layer, kind, k, width);
+    const float gp = g_packed[(size_t)c * kEbP + j];
+    if (kind == 0) {
+        const float x = r.matrix[layer][(size_t)c * width + k];
+        // d softplus / dx = sigmoid(x) (ATen: z = exp(x); x > threshold ? g : g * z / (z + 1))
+        const float z = expf(x);
+        if (g.matrix[layer]) g.matrix[layer][(size_t)c * width + k] = x > 20.0f ? gp : gp * z / (z + 1.0f);
+    } else if (kind == 1) {
+        if (g.bias[layer]) g.bias[layer][(size_t)c * width + k] = gp;
+    } else if (kind == 2) {
+        const float t = tanhf(r.factor[layer][(size_t)c * width + k]);
+        if (g.factor[layer]) g.factor[layer][(size_t)c * width + k] = gp * (1.0f - t * t);
+    } else if (kind == 3) {
+        if (g.quantiles) {
+            g.quantiles[(size_t)c * 3 + 0] = 0.0f;
+            g.quantiles[(size_t)c * 3 + 1] = gp;
+            g.quantiles[(size_t)c * 3 + 2] = 0.0f;
+        }
+    }
+}
+}  // namespace dsvc
+
+extern "C" int dsvc_eb_pack_f32(const float* const* raw15, float* packed, int C, void* stream) {
+    DSVC_CHECK_ARG(raw15 && packed && C >= 0);
+    if (C == 0) return 0;
+    dsvc::EbRaw r;
+    for (int i = 0; i < 5; ++i) { r.matrix[i] = raw15[i]; r.bias[i] = raw15[5 + i]; }
+    for (int i = 0; i < 4; ++i) r.factor[i] = raw15[10 + i];
+    r.quantiles = raw15[14];
+    for (int i = 0; i < 15; ++i) DSVC_CHECK_ARG(raw15[i] != nullptr);
+    dsvc::eb_pack_kernel<<<(unsigned)C, 64, 0, (cudaStream_t)stream>>>(r, packed, C);
+    DSVC_RETURN_LAST();
+}
+
+extern "C" int dsvc_eb_pack_bwd_f32(const float* const* raw15, const float* grad_packed, float* const* grad_raw15,
+                                    int C, void* stream) {
+    DSVC_CHECK_ARG(raw15 && grad_packed && grad_raw15 && C >= 0);
+    if (C == 0) return 0;
+    dsvc::EbRaw r;
+    dsvc::EbRawGrad g;
+    for (int i = 0; i < 5; ++i) {
+        r.matrix[i] = raw15[i]; r.bias[i] = raw15[5 + i];
+        g.matrix[i] = grad_raw15[i]; g.bias[i] = grad_raw15[5 + i];
+    }
+    for (int i = 0; i < 4; ++i) { r.factor[i] = raw15[10 + i]; g.factor[i] = grad_raw15[10 + i]; }
+    r.quantiles = raw15[14];
+    g.quantiles = grad_raw15[14];
+    for (int i = 0; i < 15; ++i) DSVC_CHECK_ARG(raw15[i] != nullptr);
+    dsvc::eb_pack_bwd_kernel<<<(unsigned)C, 64, 0, (cudaStream_t)stream>>>(r, grad_packed, g, C);
+    DSVC_RETURN_LAST();
+}
+
 extern "C" int dsvc_abi_version(void) { return DSVC_ABI_VERSION; }
 
 extern "C" const char* dsvc_error_string(int err) { return cudaGetErrorString((cudaError_t)err); }

@@ -218,6 +218,17 @@ int dsvc_gc_bwd_f32(const float* grad_lik, const float* x, const float* scales,
  * median; see deepsvc_b200/entropy.py::pack_bottleneck_params. */
 #define DSVC_EB_PARAMS_PER_CHANNEL 60
 
+/* The packed parameters of dsvc_eb_*: [C, DSVC_EB_PARAMS_PER_CHANNEL] from the module's 15 raw
+ * tensors in one launch, and the gradients of the raw tensors from the packed gradient in one
+ * more (compressai EntropyBottleneck._logits_cumulative applies softplus to `_matrix{i}` and tanh to
+ * `_factor{i}` on every call; `_get_medians()` = quantiles[:, :, 1:2]).  raw15 / grad_raw15: HOST
+ * arrays of 15 DEVICE pointers in the order _matrix0..4 ([C,f_{i+1},f_i], f = 1,3,3,3,3,1), _bias0..4
+ * ([C,f_{i+1},1]), _factor0..3 ([C,f_{i+1},1]), quantiles ([C,1,3]); a NULL grad_raw15 entry is
+ * skipped.  Contiguous fp32. */
+int dsvc_eb_pack_f32(const float* const* raw15, float* packed, int C, void* stream);
+int dsvc_eb_pack_bwd_f32(const float* const* raw15, const float* grad_packed,
+                         float* const* grad_raw15, int C, void* stream);
+
 /* Fused factorised-prior quantise / likelihood / bit estimate on z [B,C,S]
  * (S = h*w, NCHW).  Replaces compressai 1.2.1 EntropyBottleneck.forward
  * (call site image_model.py:155) and the z part of image_model.py:160-162:

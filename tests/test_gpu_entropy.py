@@ -303,3 +303,42 @@ def test_iframe_codec_shapes_f4(oracle, hw):
     assert abs(bits_got - bits_ref) <= 1e-4 * abs(bits_ref)
     assert abs(fused - bits_ref) <= 1e-4 * abs(bits_ref)
     assert math.isfinite(fused)
+
+
+def test_bottleneck_parameter_packing_fused_vs_eager():
+    """dsvc_eb_pack_f32 / _bwd_f32 (one launch each way) against the eager torch chain it replaces
+    (softplus / tanh / cat of the 15 raw tensors) and its autograd."""
+    import torch.nn.functional as F
+    import deepsvc_b200 as d
+    from deepsvc_b200.entropy import pack_bottleneck_params
+    dev = _dev()
+    g = torch.Generator().manual_seed(4)
+    eb = d.EntropyBottleneck(7)
+    with torch.no_grad():
+        for p in eb.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 2)
+        eb._matrix0[0, 0, 0] = 25.0       # softplus threshold branch
+    eb = eb.to(dev)
+
+    def eager():
+        C, parts = eb.channels, []
+        for i in range(5):
+            parts.append(F.softplus(getattr(eb, f"_matrix{i}")).reshape(C, -1))
+            parts.append(getattr(eb, f"_bias{i}").reshape(C, -1))
+            if i < 4:
+                parts.append(torch.tanh(getattr(eb, f"_factor{i}")).reshape(C, -1))
+        parts.append(eb.quantiles[:, 0, 1:2])
+        parts.append(torch.zeros(C, 1, device=dev))
+        return torch.cat(parts, 1)
+
+    cot = torch.randn(7, 60, generator=g).to(dev)
+    want = eager()
+    want.backward(cot)
+    ref_grads = [p.grad.clone() for p in eb.parameters()]
+    for p in eb.parameters():
+        p.grad = None
+    got = pack_bottleneck_params(eb)
+    assert torch.equal(got, want.detach())
+    got.backward(cot)
+    for p, r in zip(eb.parameters(), ref_grads):
+        assert torch.allclose(p.grad, r, rtol=1e-6, atol=1e-7)
