@@ -54,7 +54,7 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
     const unsigned lane = threadIdx.x, wy = threadIdx.y;
     const unsigned W = p.W, H = p.H, plane = H * W;  // C*H*W < 2^31 (checked by the launcher)
     float fx[PX], fy[PX];
-    __shared__ unsigned s_claim[2];
+    __shared__ uint4 s_claim[2];   // claimed tile: (index, tx, ty, b), decoded once by the claiming thread
     pdl_prologue();
     struct Tile { unsigned tx, ty, b; };
     auto decode = [&](unsigned t, Tile& q) {
@@ -63,15 +63,34 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
         q.b = r / tiles_y;
         q.ty = r - q.b * tiles_y;
     };
+    // static order (no scheduler state): tile coordinates advance by gridDim.x without divisions
+    const unsigned step_r = gridDim.x / tiles_x, step_x = gridDim.x - step_r * tiles_x;
+    const unsigned step_b = step_r / tiles_y, step_y = step_r - step_b * tiles_y;
     unsigned n_claims = 0;
-    // the tile after `t`: the next one off the counter, or the grid stride without scheduler state
-    auto next_tile = [&](unsigned t) -> unsigned {
-        if (!sched) return t + gridDim.x;
+    // the tile after (t, q): the next one off the counter, or the grid stride
+    auto next_tile = [&](unsigned t, Tile& q) -> unsigned {
+        if (!sched) {
+            q.tx += step_x;
+            const unsigned cx = q.tx >= tiles_x ? 1u : 0u;
+            q.tx -= cx ? tiles_x : 0u;
+            q.ty += step_y + cx;
+            const unsigned cy = q.ty >= tiles_y ? 1u : 0u;
+            q.ty -= cy ? tiles_y : 0u;
+            q.b += step_b + cy;
+            return t + gridDim.x;
+        }
         const unsigned slot = n_claims & 1u;
-        if (lane == 0 && wy == 0) s_claim[slot] = (unsigned)atomicAdd(&sched->next, 1);
+        if (lane == 0 && wy == 0) {
+            const unsigned c = (unsigned)atomicAdd(&sched->next, 1);
+            Tile d;
+            decode(c, d);
+            s_claim[slot] = make_uint4(c, d.tx, d.ty, d.b);
+        }
         __syncthreads();  // (two slots: a warp still reading the previous claim is never overwritten)
         ++n_claims;
-        return s_claim[slot];
+        const uint4 c = s_claim[slot];
+        q.tx = c.y; q.ty = c.z; q.b = c.w;
+        return c.x;
     };
     auto load_flow = [&](const Tile& q) {
         const unsigned x = q.tx * 32 + lane, y0 = q.ty * (8 * PX) + wy;
@@ -84,9 +103,14 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
             fy[j] = __ldg(fl + (pix + plane));
         }
     };
-    unsigned t = sched ? next_tile(0u) : blockIdx.x;
     Tile next;
-    decode(t, next);
+    unsigned t;
+    if (sched) {
+        t = next_tile(0u, next);
+    } else {
+        t = blockIdx.x;
+        decode(t, next);
+    }
     if (t < total_tiles) load_flow(next);
     while (t < total_tiles) {
         const Tile cur = next;
@@ -94,8 +118,7 @@ warp_fwd_nchw_fewch(const float* __restrict__ in, const float* __restrict__ flow
         float cfx[PX], cfy[PX];
 #pragma unroll
         for (int j = 0; j < PX; ++j) { cfx[j] = fx[j]; cfy[j] = fy[j]; }
-        t = next_tile(t);
-        decode(t, next);
+        t = next_tile(t, next);
         if (t < total_tiles) load_flow(next);  // in flight during this tile
         const float* inb = in + (size_t)b * C * plane;
         float* outb = out + (size_t)b * C * plane;
