@@ -8,6 +8,10 @@
 
 namespace dsvc {
 
+// Launch-level choice between the staged and the per-pixel backward kernels, made on the device
+// by warp_bwd_scout_kernel (no host synchronisation: both kernels are enqueued, one of them exits).
+enum : int { DSVC_BWD_MODE_STAGED = 1, DSVC_BWD_MODE_DIRECT = 2 };
+
 struct BwdCoord {
     Taps t;
     float wx0, wx1, wy0, wy1;  // 1-D weights (ix_se - ix, ix - ix_nw, ...)

@@ -176,8 +176,12 @@ warp_bwd_staged_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_c
                        const float* __restrict__ in, const float* __restrict__ flow,
                        float* __restrict__ gin, float* __restrict__ gflow,
                        const float* __restrict__ lin_x, const float* __restrict__ lin_y, WarpParams p,
-                       int tiles_x, int tiles_y, int csplit, int cper, int perm_mul) {
+                       int tiles_x, int tiles_y, int csplit, int cper, int perm_mul,
+                       const int* __restrict__ mode) {
     using namespace bwd;
+    // (launch-level fallback, see dsvc_warp_bwd_ws_f32: the scout launch decided that the per-pixel
+    // kernel, enqueued right behind this one, takes the whole job)
+    if (mode && *mode == DSVC_BWD_MODE_DIRECT) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);          // NS x [in box | grad_out tile]
     float* outbox = stages + NS * STAGE_FLOATS;                  // 2 x ([BH][BW] + private slots)
@@ -531,7 +535,7 @@ static bool encode_xy_plane(CUtensorMap* tm, const float* base, const WarpParams
 // grad_input must be zero on entry (it is accumulated into); grad_flow may be uninitialised.
 int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const float* flow, float* gin,
                                 float* gflow, const float* lin_x, const float* lin_y, const WarpParams& p,
-                                bool force, cudaStream_t st) {
+                                bool force, cudaStream_t st, const int* mode) {
     if (p.W % 4 != 0 || !aligned16(input) || !aligned16(gout) || (gin && !aligned16(gin))) return -1;
     if (!force && (p.C < 8 || p.W < 64 || p.H < 16)) return -1;
     if ((long long)p.B * p.C > (1ll << 30)) return -1;
@@ -580,9 +584,9 @@ int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const flo
     const unsigned grid = (unsigned)(ntiles * csplit);
     if (gin)
         warp_bwd_staged_kernel<true><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(
-            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper, perm_mul);
+            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper, perm_mul, mode);
     else
         warp_bwd_staged_kernel<false><<<grid, bwd::THREADS, bwd::SMEM_BYTES, st>>>(
-            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper, perm_mul);
+            tm_in, tm_gout, gout, input, flow, gin, gflow, lin_x, lin_y, p, tiles_x, tiles_y, csplit, cper, perm_mul, mode);
     return (int)cudaGetLastError();
 }

@@ -238,7 +238,8 @@ __global__ void __launch_bounds__(256)
 warp_bwd_nchw(const float* __restrict__ gout, const float* __restrict__ in,
               const float* __restrict__ flow, float* __restrict__ gin,
               float* __restrict__ gflow, const float* __restrict__ lin_x,
-              const float* __restrict__ lin_y, WarpParams p) {
+              const float* __restrict__ lin_y, WarpParams p, const int* __restrict__ mode) {
+    if (mode && *mode == DSVC_BWD_MODE_STAGED) return;  // the staged kernel ahead of this launch did the job
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= p.W || y >= p.H) return;
@@ -258,7 +259,7 @@ int dsvc_warp_fwd_persist_launch(const float* input, const float* flow, float* o
 
 int dsvc_warp_bwd_staged_launch(const float* gout, const float* input, const float* flow, float* gin,
                                 float* gflow, const float* lin_x, const float* lin_y, const WarpParams& p,
-                                bool force, cudaStream_t st);  // warp_bwd_staged.cu
+                                bool force, cudaStream_t st, const int* mode = nullptr);  // warp_bwd_staged.cu
 
 static int warp_args_ok(const void* a, const void* b, const void* c, int B, int C, int H, int W,
                         const void* lx, const void* ly) {
@@ -409,12 +410,51 @@ extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, cons
     }
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B);
     if (grad_input && grad_flow)
-        warp_bwd_nchw<true, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
+        warp_bwd_nchw<true, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, nullptr);
     else if (grad_input)
-        warp_bwd_nchw<true, false><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
+        warp_bwd_nchw<true, false><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, nullptr);
     else
-        warp_bwd_nchw<false, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p);
+        warp_bwd_nchw<false, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, nullptr);
     DSVC_RETURN_LAST();
+}
+
+// One warp per 64 x 16 tile samples 32 of its pixels (an 8 x 4 grid) and votes whether the tile's
+// source bounding box fits the staged kernel's box; the last CTA to finish turns the count into
+// the launch's mode and leaves the counters zeroed.  A heuristic for speed only: both kernels are
+// correct for any flow.
+__global__ void __launch_bounds__(256)
+warp_bwd_scout_kernel(const float* __restrict__ flow, const float* __restrict__ lin_x, const float* __restrict__ lin_y,
+                      WarpParams p, int tiles_x, int tiles_y, int ntiles, int* __restrict__ state) {
+    // state[0] = mode (output), state[1] = tiles that fit, state[2] = CTAs done
+    const int lane = threadIdx.x & 31, tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int fits = 0;
+    if (tile < ntiles) {
+        const int b = tile / (tiles_x * tiles_y), r = tile - b * tiles_x * tiles_y;
+        const int tx0 = (r % tiles_x) * 64, ty0 = (r / tiles_x) * 16;
+        const int x = min(tx0 + (lane & 7) * 9, p.W - 1), y = min(ty0 + (lane >> 3) * 5, p.H - 1);
+        const size_t plane = (size_t)p.H * p.W, pix = (size_t)y * p.W + x;
+        const float* fl = flow + (size_t)b * 2 * plane;
+        const BwdCoord c = bwd_coord(__ldg(lin_x + x), __ldg(lin_y + y), __ldg(fl + pix), __ldg(fl + plane + pix), p);
+        const int mnx = __reduce_min_sync(0xffffffffu, c.t.x0), mxx = __reduce_max_sync(0xffffffffu, c.t.x0);
+        const int mny = __reduce_min_sync(0xffffffffu, c.t.y0), mxy = __reduce_max_sync(0xffffffffu, c.t.y0);
+        fits = (mxx + 1 - (mnx & ~3) + 1 <= 96 && mxy + 1 - mny + 1 <= 32) ? 1 : 0;
+    }
+    __shared__ int s_fit;
+    if (threadIdx.x == 0) s_fit = 0;
+    __syncthreads();
+    if (lane == 0 && fits) atomicAdd(&s_fit, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_fit) atomicAdd(&state[1], s_fit);
+        __threadfence();
+        if (atomicAdd(&state[2], 1) == (int)gridDim.x - 1) {
+            const int nfit = atomicAdd(&state[1], 0);
+            state[0] = (2 * nfit >= ntiles) ? DSVC_BWD_MODE_STAGED : DSVC_BWD_MODE_DIRECT;
+            state[1] = 0;
+            __threadfence();
+            state[2] = 0;
+        }
+    }
 }
 
 size_t dsvc_warp_bwd_gather_workspace(int B, int H, int W);  // warp_bwd_gather.cu
@@ -449,6 +489,36 @@ extern "C" int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, c
     if (grad_input) {
         const cudaError_t e = cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
+    }
+    // Default choice with a workspace: a scout launch estimates how many tiles the staged kernel can
+    // stage; the staged kernel and the per-pixel kernel are both enqueued and the one the scout
+    // did not pick exits at once (no host synchronisation; CUDA-graph capturable).  Under wild
+    // flows (iid displacements: no tile stageable) the staged kernel's in-kernel fallback is 20 %
+    // slower than the per-pixel kernel it imitates; under SpyNet-like flows the pair of extra
+    // launches costs ~10 us of a 0.9 ms call.
+    if (g_bwd_algo == 0 && grad_input && workspace && aligned16(workspace) &&
+        workspace_bytes >= dsvc_warp_bwd_gather_workspace(B, H, W)) {
+        WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+        const int tiles_x = (W + 63) / 64, tiles_y = (H + 15) / 16;
+        const long long ntiles = (long long)tiles_x * tiles_y * B;
+        int* state = static_cast<int*>(workspace);   // 4 ints ahead of the gather kernel's tile flags (unused here)
+        if (ntiles < (1ll << 24)) {
+            cudaError_t e = cudaMemsetAsync(state, 0, 16, st);
+            if (e != cudaSuccess) return (int)e;
+            warp_bwd_scout_kernel<<<(unsigned)((ntiles + 7) / 8), 256, 0, st>>>(flow, lin_x, lin_y, p, tiles_x, tiles_y,
+                                                                                (int)ntiles, state);
+            const int r = dsvc_warp_bwd_staged_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, false,
+                                                      st, state);
+            if (r == 0) {   // staged kernel enqueued: the per-pixel kernel behind it, gated the other way
+                dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8, B);
+                if (grad_flow)
+                    warp_bwd_nchw<true, true><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, state);
+                else
+                    warp_bwd_nchw<true, false><<<grid, block, 0, st>>>(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, state);
+                DSVC_RETURN_LAST();
+            }
+            if (r != -1) return r;
+        }
     }
     return dsvc_warp_bwd_f32(grad_out, input, flow, grad_input, grad_flow, B, C, H, W, lin_x, lin_y, sx, sy, inv_sx,
                              inv_sy, flow_mode, layout, stream);

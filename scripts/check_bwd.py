@@ -10,7 +10,8 @@ from deepsvc_b200.warp import warp_backward  # noqa: E402
 
 dev = torch.device("cuda:0")
 lib = _lib.load()
-ALGOS = {"direct": _lib.WARP_BWD_DIRECT, "staged": _lib.WARP_BWD_STAGED, "gather": _lib.WARP_BWD_GATHER}
+ALGOS = {"auto": _lib.WARP_BWD_AUTO, "direct": _lib.WARP_BWD_DIRECT, "staged": _lib.WARP_BWD_STAGED,
+         "gather": _lib.WARP_BWD_GATHER}
 
 
 def run(algo, gout, inp, flow, gi=True, gf=True):
@@ -29,7 +30,10 @@ def check(shape, kind, seed=0):
     gout = torch.randn(B, C, H, W, generator=g).to(dev)
     ref = run("direct", gout, inp, flow)
     got = run("gather", gout, inp, flow)
+    auto = run("auto", gout, inp, flow)
     torch.cuda.synchronize()
+    for a, b in zip(auto, ref):
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item()), "auto (scout + staged | direct)"
     out = []
     for a, b in zip(got, ref):
         out.append((a - b).abs().max().item() / max(1.0, b.abs().max().item()))
@@ -39,7 +43,7 @@ def check(shape, kind, seed=0):
     return max(out)
 
 
-def timeit(shape, kind, algos=("direct", "staged", "gather"), n=10):
+def timeit(shape, kind, algos=("auto", "direct", "staged", "gather"), n=10):
     B, C, H, W = shape
     g = torch.Generator().manual_seed(1)
     inp = torch.randn(B, C, H, W, generator=g).to(dev)
