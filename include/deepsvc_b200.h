@@ -108,7 +108,14 @@ int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* fl
                       int flow_mode, int layout, void* stream);
 
 /* The same gradient with a caller-provided workspace: NEITHER output needs initialising.
- * By default grad_input is zero-filled here and dsvc_warp_bwd_f32 runs.  With
+ * By default grad_input is zero-filled here and the kernel is chosen PER LAUNCH on the device
+ * (when the shape is eligible for the staged kernel and a workspace is given): a scout launch
+ * samples 32 pixels of every 64 x 16 tile of the flow, counts the tiles whose source footprint
+ * fits the staged kernel's 96 x 32 box and writes one decision word into the workspace; the staged
+ * and the per-pixel launch that follow both read it and the one not chosen exits at once (no host
+ * synchronisation, graph-capturable).  At least half the tiles stageable -> staged kernel, else
+ * the per-pixel kernel, so a wild flow costs what the per-pixel kernel costs.  Without a workspace
+ * this is dsvc_warp_bwd_f32 after a zero-fill.  With
  * dsvc_set_warp_bwd_algo(DSVC_WARP_BWD_GATHER), a `workspace` (>= dsvc_warp_bwd_workspace_bytes
  * (B,H,W) bytes, any contents; one flag byte per 64 x 16 tile, written before it is read) and an
  * eligible shape (grad_input wanted, W % 4 == 0, 16-byte aligned pointers) grad_input is

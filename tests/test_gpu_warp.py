@@ -377,6 +377,27 @@ def test_backward_staged_matches_direct_kernel():
             assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{which} {nm} {err}"
 
 
+@pytest.mark.parametrize("kind,want", [("smooth", 1), ("gentle", 1), ("stress", 2)])
+def test_backward_scout_picks_kernel_per_launch(oracle, kind, want):
+    """The default backward samples the flow on the device and runs the staged kernel when at
+    least half the 64x16 tiles fit its 96x32 staging box, the per-pixel kernel otherwise; the
+    decision word (workspace[0]) is 1 / 2 and the gradients match autograd of the reference."""
+    from deepsvc_b200 import synthetic, warp as w
+    B, C, H, W = 1, 64, 272, 480
+    g = torch.Generator().manual_seed(77)
+    inp0 = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow0 = synthetic.make_flow(kind, B, H, W, g).to(_dev())
+    gout = torch.randn(B, C, H, W, generator=g).to(_dev())
+    gin, gflow = w.warp_backward(gout, inp0, flow0, True, True)
+    ws = w._bwd_workspace(_dev(), B, H, W)
+    state = ws[:16].view(torch.int32).tolist()
+    assert state[0] == want and state[1] == 0 and state[2] == 0, state
+    inp, flow = inp0.clone().requires_grad_(True), flow0.clone().requires_grad_(True)
+    oracle.torch_warp(inp, flow).backward(gout)
+    for a, b in ((gin, inp.grad), (gflow, flow.grad)):
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+
+
 def test_backward_staged_collapsed_flow():
     """Flow that collapses a whole tile onto one source column (a destination element with 64
     taps per row: its run spans several threads' shares and is summed piecewise through
