@@ -15,7 +15,7 @@ TORCH_LIB_PATH = os.path.join(_HERE, "lib", "libdeepsvc_b200_torch.so")
 FLOW_MUL_RECIPROCAL = 0
 FLOW_TRUE_DIVIDE = 1
 WARP_AUTO, WARP_GATHER, WARP_TMA = 0, 1, 2
-WARP_BWD_AUTO, WARP_BWD_DIRECT, WARP_BWD_STAGED, WARP_BWD_GATHER = 0, 1, 2, 3
+WARP_BWD_AUTO, WARP_BWD_DIRECT, WARP_BWD_STAGED, WARP_BWD_GATHER, WARP_BWD_CELL = 0, 1, 2, 3, 4
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 EB_PARAMS_PER_CHANNEL = 60
 
@@ -37,6 +37,7 @@ SIGNATURES = {
     "dsvc_warp_bwd_ws_f32": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                      c_float, c_float, c_float, c_float, c_int, c_int, _P, c_size_t, _P]),
     "dsvc_warp_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "dsvc_warp_bwd_cell_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "dsvc_warp_fused_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P,
                                     c_float, c_float, c_float, c_float, c_int, _P]),
     "dsvc_warp_fused_slots": (c_int, [c_int, c_int, c_int]),

@@ -384,7 +384,7 @@ extern "C" size_t dsvc_warp_workspace_bytes(int B, int H, int W) {
 
 static int g_bwd_algo = 0;  // DSVC_WARP_BWD_* (dsvc_set_warp_bwd_algo: tests / profiling)
 extern "C" int dsvc_set_warp_bwd_algo(int algo) {
-    DSVC_CHECK_ARG(algo >= 0 && algo <= 3);
+    DSVC_CHECK_ARG(algo >= 0 && algo <= 4);
     g_bwd_algo = algo;
     return 0;
 }
@@ -401,7 +401,7 @@ extern "C" int dsvc_warp_bwd_f32(const float* grad_out, const float* input, cons
     cudaStream_t st = (cudaStream_t)stream;
     WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
     // 0 = auto (staged kernel when the shape is eligible), 1 = per-pixel kernel, 2 = staged forced
-    const int algo = g_bwd_algo == 3 ? 0 : g_bwd_algo;
+    const int algo = g_bwd_algo >= 3 ? 0 : g_bwd_algo;
     if (algo != 1) {
         const int r = dsvc_warp_bwd_staged_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p,
                                                   algo == 2, st);
@@ -462,6 +462,13 @@ int dsvc_warp_bwd_gather_launch(const float* gout, const float* input, const flo
                                 float* gflow, const float* lin_x, const float* lin_y, const WarpParams& p,
                                 bool force, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+size_t dsvc_warp_bwd_cell_workspace(int B, int H, int W);  // warp_bwd_cell.cu
+int dsvc_warp_bwd_cell_launch(const float* gout, const float* input, const float* flow, float* gin, float* gflow,
+                              const float* lin_x, const float* lin_y, const WarpParams& p, void* workspace,
+                              size_t workspace_bytes, cudaStream_t st);
+
+extern "C" size_t dsvc_warp_bwd_cell_workspace_bytes(int B, int H, int W) { return dsvc_warp_bwd_cell_workspace(B, H, W); }
+
 extern "C" size_t dsvc_warp_bwd_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     return dsvc_warp_bwd_gather_workspace(B, H, W);
@@ -485,6 +492,13 @@ extern "C" int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, c
                                                   g_bwd_algo == 3, workspace, workspace_bytes, st);
         if (r != -1) return r;
         if (g_bwd_algo == 3) return (int)cudaErrorInvalidValue;
+    }
+    if (grad_input && g_bwd_algo == 4) {
+        WarpParams p{B, C, H, W, sx, sy, inv_sx, inv_sy, flow_mode};
+        const int r = dsvc_warp_bwd_cell_launch(grad_out, input, flow, grad_input, grad_flow, lin_x, lin_y, p, workspace,
+                                                workspace_bytes, st);
+        if (r != -1) return r;
+        return (int)cudaErrorInvalidValue;
     }
     if (grad_input) {
         const cudaError_t e = cudaMemsetAsync(grad_input, 0, (size_t)B * C * H * W * sizeof(float), st);

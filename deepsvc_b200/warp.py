@@ -207,7 +207,7 @@ def warp_backward(grad_out, inp, flow, need_input_grad=True, need_flow_grad=True
     lin_x, lin_y = _base_grids(inp.device, H, W)
     sx, sy, inv_sx, inv_sy = _scales(H, W)
     lib = _lib.load()
-    ws = _bwd_workspace(inp.device, B, H, W) if need_input_grad else None
+    ws = _bwd_workspace(inp.device, B, H, W, big=C >= CELL_MIN_CHANNELS) if need_input_grad else None
     with torch.cuda.device(inp.device):
         err = lib.dsvc_warp_bwd_ws_f32(
             grad_out.data_ptr(), inp.data_ptr(), flow.data_ptr(), _lib.ptr(gin), _lib.ptr(gflow),
@@ -219,12 +219,15 @@ def warp_backward(grad_out, inp, flow, need_input_grad=True, need_flow_grad=True
 
 
 _bwd_ws_cache = {}
+CELL_MIN_CHANNELS = 8   # the cell-order backward (csrc/warp_bwd_cell.cu) amortises its tables over the channels
 
 
-def _bwd_workspace(device, B, H, W):
+def _bwd_workspace(device, B, H, W, big=False):
     """Per-tile flag bytes of the gather backward (written before they are read inside one
     call): one buffer per (device, stream), a fresh one under CUDA-graph capture."""
     n = _lib.load().dsvc_warp_bwd_workspace_bytes(B, H, W)
+    if big:
+        n = max(n, _lib.load().dsvc_warp_bwd_cell_workspace_bytes(B, H, W))
     if torch.cuda.is_current_stream_capturing():
         return torch.empty(n, dtype=torch.uint8, device=device)
     key = (device, torch.cuda.current_stream(device).cuda_stream)

@@ -132,6 +132,9 @@ int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, const float*
                          int flow_mode, int layout,
                          void* workspace, size_t workspace_bytes, void* stream);
 size_t dsvc_warp_bwd_workspace_bytes(int B, int H, int W);
+/* Workspace of the cell-order backward kernel (csrc/warp_bwd_cell.cu, DSVC_WARP_BWD_CELL): the
+ * per-cell pixel tables, 28 bytes per pixel plus the blocks' buckets. */
+size_t dsvc_warp_bwd_cell_workspace_bytes(int B, int H, int W);
 
 /* Fusions around the few-channel (C <= 4) warps -- SURVEY.md 8f-3, inference only.
  * Exactly one of `flow` [B,2,H,W] and `flow_coarse` [B,2,H/2,W/2] is given.
@@ -173,6 +176,7 @@ int dsvc_lrp_add_bwd_f32(const float* grad_out, const float* lrp, float* grad_lr
 #define DSVC_WARP_BWD_DIRECT 1
 #define DSVC_WARP_BWD_STAGED 2
 #define DSVC_WARP_BWD_GATHER 3 /* dsvc_warp_bwd_ws_f32 only */
+#define DSVC_WARP_BWD_CELL 4   /* dsvc_warp_bwd_ws_f32 only */
 int dsvc_set_warp_bwd_algo(int algo);
 
 /* Number of double partial sums a gc launch over rows x inner elements writes. */
