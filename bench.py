@@ -647,7 +647,7 @@ def run_cfg3(args):
     lin = dsvc.warp._base_grids(dev, Ht, Wt)
     sc = dsvc.warp._scales(Ht, Wt)
     gflow = torch.empty_like(f)
-    ws = torch.empty(_lib.load().dsvc_warp_bwd_workspace_bytes(Bt, Ht, Wt), dtype=torch.uint8, device=dev)
+    ws = dsvc.warp._bwd_workspace(dev, Bt, Ht, Wt, big=True)
     for _ in range(20):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -151,7 +151,11 @@ std::tuple<Tensor, Tensor> warp_bwd(const Tensor& grad_out_in, const Tensor& inp
     const Scales s = scales_of(H, W);
     c10::cuda::CUDAGuard guard(inp.device());
     Tensor ws;
-    if (need_input) ws = workspace(g_bwd_ws, inp, std::max<size_t>(dsvc_warp_bwd_workspace_bytes(B, H, W), 64), false);
+    if (need_input) {
+        size_t n = std::max<size_t>(dsvc_warp_bwd_workspace_bytes(B, H, W), 64);
+        if (C >= 8) n = std::max(n, dsvc_warp_bwd_cell_workspace_bytes(B, H, W));  // the cell-order kernel's tables
+        ws = workspace(g_bwd_ws, inp, n, false);
+    }
     check_err(dsvc_warp_bwd_ws_f32(grad_out.data_ptr<float>(), inp.data_ptr<float>(), flow.data_ptr<float>(),
                                    need_input ? gin.data_ptr<float>() : nullptr,
                                    need_flow ? gflow.data_ptr<float>() : nullptr, B, C, H, W,

@@ -77,11 +77,11 @@ def test_gaussian_conditional_random_shapes(B, C, h, w, nslice, training, seed):
        kind=st.sampled_from(["smooth", "stress", "border", "integer", "collapse"]), need_flow=st.booleans(),
        seed=st.integers(0, 10_000))
 def test_warp_backward_kernels_agree_random_shapes(B, C, Hq, Wq, kind, need_flow, seed):
-    """The three backward kernels -- per-pixel scatter, shared-memory staged scatter, destination-owned
-    gather + fix-up launch -- on random shapes (W a multiple of 4: the staged kernels' eligibility) and
+    """The four backward kernels -- per-pixel scatter, shared-memory staged scatter, destination-owned
+    gather + fix-up launch, cell-order -- on random shapes (W a multiple of 4: the staged kernels' eligibility) and
     flow families, incl. flows that collapse many pixels onto one source element (list overflow, flagged
     tiles): same gradients up to the fp32 summation order, grad_input needs no zero-fill."""
-    from deepsvc_b200 import _lib, synthetic
+    from deepsvc_b200 import _lib, synthetic, warp as warp_mod
     from deepsvc_b200.warp import warp_backward
     H, W = 4 * Hq, 4 * Wq
     g = torch.Generator().manual_seed(seed)
@@ -96,13 +96,17 @@ def test_warp_backward_kernels_agree_random_shapes(B, C, Hq, Wq, kind, need_flow
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     lib = _lib.load()
     res = {}
-    for name, algo in (("direct", _lib.WARP_BWD_DIRECT), ("staged", _lib.WARP_BWD_STAGED), ("gather", _lib.WARP_BWD_GATHER)):
+    for name, algo in (("direct", _lib.WARP_BWD_DIRECT), ("staged", _lib.WARP_BWD_STAGED), ("gather", _lib.WARP_BWD_GATHER),
+                       ("cell", _lib.WARP_BWD_CELL)):
         _lib.check(lib.dsvc_set_warp_bwd_algo(algo), "algo")
+        min_c = warp_mod.CELL_MIN_CHANNELS
+        warp_mod.CELL_MIN_CHANNELS = 1   # the cell-order kernel takes any C once its workspace is there
         try:
             res[name] = warp_backward(gout, inp, flow, True, need_flow)
         finally:
+            warp_mod.CELL_MIN_CHANNELS = min_c
             lib.dsvc_set_warp_bwd_algo(_lib.WARP_BWD_AUTO)
-    for name in ("staged", "gather"):
+    for name in ("staged", "gather", "cell"):
         for a, b, nm in zip(res[name], res["direct"], ("grad_input", "grad_flow")):
             if b is None:
                 assert a is None

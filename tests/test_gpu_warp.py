@@ -317,9 +317,9 @@ def _bwd_algo(algo):
 @pytest.mark.parametrize("kind", ["smooth", "stress", "border"])
 @pytest.mark.parametrize("shape", [(2, 16, 40, 64), (1, 64, 128, 192), (8, 64, 64, 64), (1, 9, 33, 100),
                                    (1, 8, 16, 68)])
-@pytest.mark.parametrize("bwd", ["staged", "gather"])
+@pytest.mark.parametrize("bwd", ["staged", "gather", "cell"])
 def test_backward_staged_vs_stock_torch_cuda(oracle, shape, kind, need, bwd):
-    """The staged / gather backward kernels (forced) against autograd of the reference function on
+    """The staged / gather / cell-order backward kernels (forced) against autograd of the reference function on
     the GPU (its GPU branch, modules.py:44-62): gradients within 1e-4 of the tensor's scale."""
     import deepsvc_b200 as d
     from deepsvc_b200 import _lib, synthetic
@@ -329,9 +329,9 @@ def test_backward_staged_vs_stock_torch_cuda(oracle, shape, kind, need, bwd):
     flow0 = synthetic.make_flow(kind, B, H, W, g).to(_dev())
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     res = []
-    if bwd == "gather" and not need[0]:
-        pytest.skip("the gather kernel produces grad_input; flow-only gradients use the other kernels")
-    forced = _lib.WARP_BWD_STAGED if bwd == "staged" else _lib.WARP_BWD_GATHER
+    if bwd in ("gather", "cell") and not need[0]:
+        pytest.skip("the gather / cell kernels produce grad_input; flow-only gradients use the other kernels")
+    forced = {"staged": _lib.WARP_BWD_STAGED, "gather": _lib.WARP_BWD_GATHER, "cell": _lib.WARP_BWD_CELL}[bwd]
     for fn, algo in ((oracle.torch_warp, _lib.WARP_BWD_AUTO), (d.torch_warp, forced)):
         _bwd_algo(algo)
         try:
@@ -361,7 +361,7 @@ def test_backward_staged_matches_direct_kernel():
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     out = {}
     for name, algo in (("direct", _lib.WARP_BWD_DIRECT), ("staged", _lib.WARP_BWD_STAGED),
-                       ("gather", _lib.WARP_BWD_GATHER)):
+                       ("gather", _lib.WARP_BWD_GATHER), ("cell", _lib.WARP_BWD_CELL)):
         _bwd_algo(algo)
         try:
             out[name] = warp_backward(gout, inp, flow, True, True)
@@ -371,31 +371,69 @@ def test_backward_staged_matches_direct_kernel():
         # bilinear weights of a pixel sum to 1: every plane of grad_input sums to H*W
         s = ones.double().sum((2, 3))
         assert (s - H * W).abs().max().item() <= 1e-3 * H * W, name
-    for which in ("staged", "gather"):
+    for which in ("staged", "gather", "cell"):
         for a, b, nm in zip(out[which], out["direct"], ("grad_input", "grad_flow")):
             err = (a - b).abs().max().item()
             assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{which} {nm} {err}"
 
 
 @pytest.mark.parametrize("kind,want", [("smooth", 1), ("gentle", 1), ("stress", 2)])
-def test_backward_scout_picks_kernel_per_launch(oracle, kind, want):
-    """The default backward samples the flow on the device and runs the staged kernel when at
-    least half the 64x16 tiles fit its 96x32 staging box, the per-pixel kernel otherwise; the
-    decision word (workspace[0]) is 1 / 2 and the gradients match autograd of the reference."""
+def test_backward_scout_picks_kernel_per_launch(oracle, kind, want, monkeypatch):
+    """With a workspace too small for the cell tables the default backward samples the flow on the
+    device and runs the staged kernel when at least half the 64x16 tiles fit its 96x32 staging box,
+    the per-pixel kernel otherwise; the decision word (workspace[0]) is 1 / 2 and the gradients
+    match autograd of the reference."""
     from deepsvc_b200 import synthetic, warp as w
+    monkeypatch.setattr(w, "CELL_MIN_CHANNELS", 1 << 30)   # small workspace: no cell tables
+    w._bwd_ws_cache.clear()
     B, C, H, W = 1, 64, 272, 480
     g = torch.Generator().manual_seed(77)
     inp0 = torch.randn(B, C, H, W, generator=g).to(_dev())
     flow0 = synthetic.make_flow(kind, B, H, W, g).to(_dev())
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
-    gin, gflow = w.warp_backward(gout, inp0, flow0, True, True)
-    ws = w._bwd_workspace(_dev(), B, H, W)
-    state = ws[:16].view(torch.int32).tolist()
+    try:
+        gin, gflow = w.warp_backward(gout, inp0, flow0, True, True)
+        ws = w._bwd_workspace(_dev(), B, H, W)
+        state = ws[:16].view(torch.int32).tolist()
+    finally:
+        w._bwd_ws_cache.clear()
     assert state[0] == want and state[1] == 0 and state[2] == 0, state
     inp, flow = inp0.clone().requires_grad_(True), flow0.clone().requires_grad_(True)
     oracle.torch_warp(inp, flow).backward(gout)
     for a, b in ((gin, inp.grad), (gflow, flow.grad)):
         assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize("kind", ["smooth", "stress", "border", "gentle"])
+@pytest.mark.parametrize("shape", [(1, 64, 272, 480), (2, 8, 100, 132), (1, 16, 31, 31), (1, 8, 7, 200), (3, 9, 64, 33)])
+def test_backward_cell_order_is_the_default_for_wide_warps(oracle, shape, kind):
+    """C >= 8 with the full workspace: the cell-order kernel (csrc/warp_bwd_cell.cu) runs by default --
+    grad_input is NOT pre-zeroed by anyone (poisoned here) and every element must be written; both
+    gradients against autograd of the reference on the GPU, for flows that fill cells unevenly
+    (stress: Poisson occupancy; border: hundreds of pixels clamped into one cell -> overflow list)."""
+    from deepsvc_b200 import _lib, synthetic, warp as w
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    inp0 = torch.randn(B, C, H, W, generator=g).to(_dev())
+    flow0 = synthetic.make_flow(kind, B, H, W, g).to(_dev())
+    gout = torch.randn(B, C, H, W, generator=g).to(_dev())
+    lib = _lib.load()
+    lin_x, lin_y = w._base_grids(_dev(), H, W)
+    sx, sy, inv_sx, inv_sy = w._scales(H, W)
+    ws = w._bwd_workspace(_dev(), B, H, W, big=True)
+    assert ws.numel() >= lib.dsvc_warp_bwd_cell_workspace_bytes(B, H, W)
+    gin = torch.full_like(inp0, float("nan"))
+    gflow = torch.full_like(flow0, float("nan"))
+    _lib.check(lib.dsvc_warp_bwd_ws_f32(gout.data_ptr(), inp0.data_ptr(), flow0.data_ptr(), gin.data_ptr(), gflow.data_ptr(),
+                                        B, C, H, W, lin_x.data_ptr(), lin_y.data_ptr(), sx, sy, inv_sx, inv_sy,
+                                        _lib.FLOW_MUL_RECIPROCAL, _lib.LAYOUT_NCHW, ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream(_dev()).cuda_stream), "dsvc_warp_bwd_ws_f32")
+    inp, flow = inp0.clone().requires_grad_(True), flow0.clone().requires_grad_(True)
+    oracle.torch_warp(inp, flow).backward(gout)
+    assert torch.isfinite(gin).all() and torch.isfinite(gflow).all()
+    for a, b, nm in ((gin, inp.grad, "grad_input"), (gflow, flow.grad, "grad_flow")):
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), f"{nm} {err}"
 
 
 def test_backward_staged_collapsed_flow():
@@ -412,7 +450,7 @@ def test_backward_staged_collapsed_flow():
     flow0 = flow0.to(_dev())
     gout = torch.randn(B, C, H, W, generator=g).to(_dev())
     res = []
-    for algo in (_lib.WARP_BWD_DIRECT, _lib.WARP_BWD_STAGED, _lib.WARP_BWD_GATHER):
+    for algo in (_lib.WARP_BWD_DIRECT, _lib.WARP_BWD_STAGED, _lib.WARP_BWD_GATHER, _lib.WARP_BWD_CELL):
         _bwd_algo(algo)
         try:
             inp = inp0.clone().requires_grad_(True)
