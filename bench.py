@@ -677,10 +677,10 @@ def run_cfg3(args):
                                      "the path's own parameters (two EntropyBottlenecks): real p.grad views in flat buckets, NCCL "
                                      "all-reduce + mean + clamp inside the timed region; the whole-model all-reduce overlapped with "
                                      "backward is `--workload dropin --train`")},
-            "roofline": {"bound": "hbm", "kernel": "warp_bwd_staged (64-ch, both gradients, 8x256x256)", "achieved": ach,
+            "roofline": {"bound": "hbm", "kernel": "warp_bwd_cell_staged (64-ch, both gradients, 8x256x256)", "achieved": ach,
                          "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": nb["feature_bwd"], "kernel_ms": k_ms,
-                         "note": "whole dsvc_warp_bwd_ws_f32 call (zero-fill of grad_input + staged kernel), L2 flushed",
+                         "note": "whole dsvc_warp_bwd_ws_f32 call (table memsets + cell_build + cell-order kernel + overflow launch), L2 flushed",
                          "whole_step": {"algorithmic_bytes": nb["total"],
                                         "achieved_gbs": nb["total"] * args.steps / (ms * 1e-3) / 1e9}},
             "cpu_baseline": None, "e2e": None, "clocks": sampler.summary()}), flush=True)
