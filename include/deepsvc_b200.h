@@ -108,22 +108,26 @@ int dsvc_warp_bwd_f32(const float* grad_out, const float* input, const float* fl
                       int flow_mode, int layout, void* stream);
 
 /* The same gradient with a caller-provided workspace: NEITHER output needs initialising.
- * By default grad_input is zero-filled here and the kernel is chosen PER LAUNCH on the device
- * (when the shape is eligible for the staged kernel and a workspace is given): a scout launch
- * samples 32 pixels of every 64 x 16 tile of the flow, counts the tiles whose source footprint
- * fits the staged kernel's 96 x 32 box and writes one decision word into the workspace; the staged
- * and the per-pixel launch that follow both read it and the one not chosen exits at once (no host
- * synchronisation, graph-capturable).  At least half the tiles stageable -> staged kernel, else
- * the per-pixel kernel, so a wild flow costs what the per-pixel kernel costs.  Without a workspace
- * this is dsvc_warp_bwd_f32 after a zero-fill.  With
- * dsvc_set_warp_bwd_algo(DSVC_WARP_BWD_GATHER), a `workspace` (>= dsvc_warp_bwd_workspace_bytes
+ * Kernel choice (DSVC_WARP_BWD_AUTO):
+ *  - C >= 8, grad_input wanted and workspace_bytes >= dsvc_warp_bwd_cell_workspace_bytes(B,H,W): the
+ *    cell-order kernel (csrc/warp_bwd_cell.cu).  A table launch files every output pixel under the
+ *    cell (floor of its clamped source coordinate) it samples; one warp per 31 x 2 block of grad_input
+ *    then walks the cells: per channel, loads from a TMA-staged box of grad_out and the input rows,
+ *    shuffles, plain row stores -- no atomics on the main path, no zero-fill, any flow (cells with
+ *    more than two pixels and wild regions take reduction / load paths inside the same launches).
+ *  - otherwise grad_input is zero-filled here and, when the shape is eligible for the staged kernel
+ *    and workspace_bytes >= dsvc_warp_bwd_workspace_bytes, the kernel is chosen PER LAUNCH on the
+ *    device: a scout launch samples 32 pixels of every 64 x 16 tile of the flow, counts the tiles whose
+ *    source footprint fits the staged kernel's 96 x 32 box and writes one decision word into the
+ *    workspace; the staged and the per-pixel launch that follow both read it and the one not chosen
+ *    exits at once (no host synchronisation, graph-capturable).
+ *  - without a workspace this is dsvc_warp_bwd_f32 after a zero-fill.
+ * With dsvc_set_warp_bwd_algo(DSVC_WARP_BWD_GATHER), a `workspace` (>= dsvc_warp_bwd_workspace_bytes
  * (B,H,W) bytes, any contents; one flag byte per 64 x 16 tile, written before it is read) and an
  * eligible shape (grad_input wanted, W % 4 == 0, 16-byte aligned pointers) grad_input is
- * produced by the destination-owned gather kernel (csrc/warp_bwd_gather.cu: per-tile tap lists
- * in registers, TMA-staged grad_out box, one plain store per element, no atomics, no zero-fill)
- * followed by a fix-up launch for the taps outside a tile's search region; an ineligible shape
- * is cudaErrorInvalidValue.  The gather kernel is opt-in: measured on B200 it ties the staged
- * kernel at 1080p and loses at the training shape. */
+ * produced by the destination-owned gather kernel (csrc/warp_bwd_gather.cu); an ineligible shape
+ * is cudaErrorInvalidValue.  DSVC_WARP_BWD_CELL forces the cell-order kernel (cudaErrorInvalidValue
+ * when the workspace is too small).  The workspace may hold anything on entry and is scratch. */
 int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, const float* flow,
                          float* grad_input, float* grad_flow,
                          int B, int C, int H, int W,
@@ -132,8 +136,8 @@ int dsvc_warp_bwd_ws_f32(const float* grad_out, const float* input, const float*
                          int flow_mode, int layout,
                          void* workspace, size_t workspace_bytes, void* stream);
 size_t dsvc_warp_bwd_workspace_bytes(int B, int H, int W);
-/* Workspace of the cell-order backward kernel (csrc/warp_bwd_cell.cu, DSVC_WARP_BWD_CELL): the
- * per-cell pixel tables, 28 bytes per pixel plus the blocks' buckets. */
+/* Workspace that enables the cell-order backward kernel (csrc/warp_bwd_cell.cu): the per-cell pixel
+ * tables, 28 bytes per pixel plus the regions' buckets (76 MB at 1 x 1088 x 1920). */
 size_t dsvc_warp_bwd_cell_workspace_bytes(int B, int H, int W);
 
 /* Fusions around the few-channel (C <= 4) warps -- SURVEY.md 8f-3, inference only.
