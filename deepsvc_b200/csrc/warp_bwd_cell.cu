@@ -487,6 +487,10 @@ __host__ __device__ constexpr int s_in_rows(int R) { return CTA_BY * R + 1; }
 __host__ __device__ constexpr int s_g_bytes(int R) { return (GL_W * gl_h(R) * 4 + 127) & ~127; }  // the zero words sit behind it
 __host__ __device__ constexpr int s_stage_bytes(int R) { return (s_g_bytes(R) + 128 + IP * s_in_rows(R) * 4 + 127) & ~127; }
 
+// The compiler re-materialises shared-window addresses and index arithmetic inside the channel loop
+// rather than spend a register on them (~30 of 155 instructions per channel); an empty asm makes the
+// value opaque, so it stays where it is.
+__device__ __forceinline__ void keep_in_register(unsigned& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ float lds_at(unsigned addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -611,14 +615,22 @@ warp_bwd_cell_staged_kernel(const __grid_constant__ CUtensorMap tm_gs, const __g
                         a = (unsigned)(((py - by0) * pitch + (px - bx0)) * 4);
                     }
                     sa[lr][e] = ring_s + a;
+                    keep_in_register(sa[lr][e]);
                 }
-            const unsigned ia = ring_s + (unsigned)(S_IN + ((Yb - Yr) * IP + (X + 1 - ix0)) * 4);
+            unsigned ia = ring_s + (unsigned)(S_IN + ((Yb - Yr) * IP + (X + 1 - ix0)) * 4);
+            unsigned full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), o_out_r = o_out;
+            unsigned st_rows = st_col ? (unsigned)max(rows_out, 0) : 0u;  // rows this lane stores
+            keep_in_register(ia);
+            keep_in_register(full0);
+            keep_in_register(empty0);
+            keep_in_register(o_out_r);
+            keep_in_register(st_rows);
             float* ob = gin + ((size_t)b * p.C + c0) * plane;
             for (int i0 = 0; c0 + i0 < c1; i0 += NS) {
                 static_for<NS>([&](auto sc) {
                     constexpr int s = decltype(sc)::value;
                     if (c0 + i0 + s < c1) {
-                        mbar_wait(smem_u32(&full_bar[s]), (unsigned)((i0 / NS) & 1));
+                        mbar_wait(full0 + 8 * s, (unsigned)((i0 / NS) & 1));
                         float g[R + 1][2], inR[R + 1];
 #pragma unroll
                         for (int lr = 0; lr <= R; ++lr)
@@ -628,12 +640,26 @@ warp_bwd_cell_staged_kernel(const __grid_constant__ CUtensorMap tm_gs, const __g
 #pragma unroll
                             for (int k = 0; k <= R; ++k) inR[k] = lds_at(ia + s * STAGE + k * IP * 4);
                         }
-                        cell_channel<R, NEED_GFLOW>(g, inR, wx, wy, gx, gy, ob, o_out, st_col, rows_out, W);
+                        cell_channel<R, NEED_GFLOW>(g, inR, wx, wy, gx, gy, ob, o_out_r, true, (int)st_rows, W);
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));
+                        if (lane == 0) mbar_arrive(empty0 + 8 * s);
                         ob += plane;
                     }
                 });
+            }
+            if (NEED_GFLOW && lane >= 1) {
+                // the pixel index back from its shared-window address (the table words are not kept live)
+#pragma unroll
+                for (int lr = 1; lr <= R; ++lr)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned a = (sa[lr][e] - ring_s) >> 2;
+                        if (a != (unsigned)(S_ZERO >> 2)) {
+                            const unsigned row = a / (unsigned)pitch, col = a - row * (unsigned)pitch;
+                            cell_put_gflow(gflow, p, b, csplit > 1, (unsigned)((by0 + (int)row) * W + bx0 + (int)col),
+                                           (clampb >> (lr * 4 + e * 2)) & 3u, gx[lr - 1][e], gy[lr - 1][e]);
+                        }
+                    }
             }
         }
     } else if (active) {
@@ -659,15 +685,14 @@ warp_bwd_cell_staged_kernel(const __grid_constant__ CUtensorMap tm_gs, const __g
             ib += plane;
             ob += plane;
         }
-    }
-
-    if (NEED_GFLOW && active && lane >= 1) {
+        if (NEED_GFLOW && lane >= 1) {
 #pragma unroll
-        for (int lr = 1; lr <= R; ++lr) {
+            for (int lr = 1; lr <= R; ++lr) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-                if (off[lr][e] != NOPIX)
-                    cell_put_gflow(gflow, p, b, csplit > 1, off[lr][e], (clampb >> (lr * 4 + e * 2)) & 3u, gx[lr - 1][e], gy[lr - 1][e]);
+                for (int e = 0; e < 2; ++e)
+                    if (off[lr][e] != NOPIX)
+                        cell_put_gflow(gflow, p, b, csplit > 1, off[lr][e], (clampb >> (lr * 4 + e * 2)) & 3u, gx[lr - 1][e], gy[lr - 1][e]);
+            }
         }
     }
     cell_region_extras<R, NEED_GFLOW>(gout, in, gin, gflow, counts, bent, p, b, c0, c1, csplit > 1);
