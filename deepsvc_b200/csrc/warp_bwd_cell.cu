@@ -923,10 +923,10 @@ int dsvc_warp_bwd_cell_launch(const float* gout, const float* input, const float
 #undef DSVC_CELL_GO
     if (e != cudaSuccess) return (int)e;
     if (gflow)
-        cell_fixup_kernel<true><<<DSVC_NUM_SMS, 256, 0, st>>>(gout, input, flow, gin, gflow, lin_x, lin_y, p, counts, ovf,
+        cell_fixup_kernel<true><<<2 * DSVC_NUM_SMS, 256, 0, st>>>(gout, input, flow, gin, gflow, lin_x, lin_y, p, counts, ovf,
                                                                   CTA_BY * R);
     else
-        cell_fixup_kernel<false><<<DSVC_NUM_SMS, 256, 0, st>>>(gout, input, flow, gin, gflow, lin_x, lin_y, p, counts, ovf,
+        cell_fixup_kernel<false><<<2 * DSVC_NUM_SMS, 256, 0, st>>>(gout, input, flow, gin, gflow, lin_x, lin_y, p, counts, ovf,
                                                                    CTA_BY * R);
     return (int)cudaGetLastError();
 }
