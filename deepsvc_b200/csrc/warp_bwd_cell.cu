@@ -40,8 +40,14 @@ namespace dsvc {
 namespace bcell {
 
 constexpr int DC = 31;  // columns of grad_input per warp (lane 0 is the halo column of cells)
-constexpr int WARPS = 8, THREADS = WARPS * 32;
-constexpr int CTA_BX = 2, CTA_BY = 4;  // a CTA's warps cover a region of 62 x 4R elements
+#ifndef DSVC_CELL_CTA_BY
+#define DSVC_CELL_CTA_BY 4
+#endif
+#ifndef DSVC_CELL_STAGED_MINB
+#define DSVC_CELL_STAGED_MINB 3  // CTAs per SM of the staged variant (R = 2)
+#endif
+constexpr int CTA_BX = 2, CTA_BY = DSVC_CELL_CTA_BY;  // a CTA's warps cover a region of 62 x CTA_BY R elements
+constexpr int WARPS = CTA_BX * CTA_BY, THREADS = WARPS * 32;
 constexpr int RX = CTA_BX * DC;
 constexpr int EC = THREADS;            // bucket entries per region: one thread each
 constexpr int D = 4;                   // channels in flight per thread (cp.async ring variant)
@@ -903,7 +909,7 @@ int dsvc_warp_bwd_cell_launch(const float* gout, const float* input, const float
         else if (minb == 2) DSVC_CELL_GO_STAGED(2, 2);
         else
 #endif
-        DSVC_CELL_GO_STAGED(2, 3);
+        DSVC_CELL_GO_STAGED(2, DSVC_CELL_STAGED_MINB);
     }
     if (e == cudaErrorNotSupported) {  // unaligned rows or no tensor-map encoder: the load variant
 #ifdef DSVC_TUNE
