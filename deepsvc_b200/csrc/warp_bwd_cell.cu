@@ -16,7 +16,7 @@
 // The only irregular access left is one load of grad_out per pixel and channel (pixels of
 // adjacent cells are adjacent up to the flow's local distortion: near-coalesced, served by L1).
 //
-// Launches of one call (dsvc_warp_bwd_cell_launch):
+// Launches of one call (dsvc_warp_bwd_cell_launch), after two memsets (tables 0xFF, counters 0):
 //   1. cell_build_kernel, one thread per output pixel: coordinates as in the forward (bit-exact
 //      op order, warp_bwd_common.cuh), then the pixel claims layer 0 or 1 of its cell's table
 //      entry by atomicCAS (pixel index + clamp flags, weights beside it).  A third, fourth ...
@@ -24,14 +24,19 @@
 //      62 x 4R region of grad_input (one CTA of the next launch) that one of its taps reaches;
 //      with a full bucket it goes to the launch-wide overflow list with the mask of the regions
 //      that refused it.
-//   2. warp_bwd_cell_kernel: one warp per 31 x R block of grad_input (+1 halo column / row of
-//      cells), lane = cell column; two table layers in registers; per channel 2(R+1) loads of
-//      grad_out, R+1 row loads of the input, 3R+2 shuffles, R row stores.  After the CTA's warps
-//      have stored their blocks, one thread per bucket entry walks the channels and adds the
-//      extra's taps inside the region with RED.ADD (and computes its grad_flow).
+//   2. the gradients, one warp per 31 x R block of grad_input (+1 halo column / row of cells),
+//      lane = cell column, two table layers in registers, per channel 3R+2 shuffles and R row stores:
+//      warp_bwd_cell_staged_kernel (default; section 2b) reads its 2(R+1) grad_out values and R+1
+//      input values per channel with LDS from a TMA-fed ring; warp_bwd_cell_kernel (rows that are
+//      not 16-byte multiples) with predicated global loads.  After a CTA's warps have stored their
+//      blocks, its threads split (bucket entry, channel chunk) and add the extras' taps inside
+//      the region with RED.ADD (and compute their grad_flow).
 //   3. cell_fixup_kernel: the overflow list (empty for SpyNet-like flows), one warp per entry,
 //      per-pixel scatter of exactly the taps nobody else took.
-// Any flow is handled; the speed degrades towards the per-pixel kernel as cells fill up.
+// Any flow is handled; the speed degrades towards the per-pixel kernel as cells fill up.  Like
+// ATen's kernel the result is not bit-reproducible from run to run: which of a cell's pixels
+// gets layer 0 is decided by the atomicCAS race, which permutes fp32 sums of two to four terms.
+// Measured variants and what bounds the kernel: DESIGN.md 4.3.0, profiles/r02_bwd_cell_timing.txt.
 #include "warp_bwd_common.cuh"
 #include "tma_utils.cuh"
 #include <cstdlib>
