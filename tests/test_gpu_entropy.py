@@ -263,22 +263,25 @@ def test_full_size_1080p_checksum(oracle):
     assert int(idx.min()) >= 0 and int(idx.max()) <= 63
 
 
-@pytest.mark.parametrize("hw", [(16, 28), (68, 120)])
-def test_iframe_codec_shapes_f4(oracle, hw):
-    """the I-frame codec (ICIP2020ResB, image_model.py:440-488) calls the same ops
-    at M = 320 (10 slices x 32 channels) and N = 192 hyper-latent channels.  y_hat / z_hat
-    bit-exact, bits within 1e-4 relative, for the eval path and the fused bit-sum path."""
+@pytest.mark.parametrize("case", [("ICIP2020ResB", 1, 320, 192, 10, 16, 28), ("ICIP2020ResB", 1, 320, 192, 10, 68, 120),
+                                  ("cFeatureCompress", 4, 72, 72, 6, 16, 16)])
+def test_iframe_codec_shapes_f4(oracle, case):
+    """the I-frame codec (ICIP2020ResB, image_model.py:440-488: M = 320 = 10 slices x 32
+    channels, N = 192 hyper-latent channels) and the semantic layer's cFeatureCompress
+    (semantic_layer.py:1189-1200,1324-1372: N = 72 = 6 slices x 12 channels, batch 4 of 256^2 crops ->
+    y [4,72,16,16], z [4,72,4,4]) call the same ops in the same pattern.  y_hat / z_hat bit-exact, bits
+    within 1e-4 relative, for the eval path and the fused bit-sum path."""
     import math
     import deepsvc_b200 as dsvc
     from deepsvc_b200 import synthetic
     dev = torch.device("cuda:0")
-    h, w = hw
-    g = torch.Generator().manual_seed(320 + h)
-    y, scales, means = synthetic.make_latents(1, 320, h, w, g)
-    z = torch.randn(1, 192, max(h // 4, 1), max(w // 4, 1), generator=g) * 3.0
-    eb_o, gc_o = oracle.make_entropy_models(192, seed=192)
+    _, B, M, N, n_slices, h, w = case
+    g = torch.Generator().manual_seed(M + h)
+    y, scales, means = synthetic.make_latents(B, M, h, w, g)
+    z = torch.randn(B, N, max(h // 4, 1), max(w // 4, 1), generator=g) * 3.0
+    eb_o, gc_o = oracle.make_entropy_models(N, seed=N)
     eb_o.eval(), gc_o.eval()
-    eb = dsvc.EntropyBottleneck(192)
+    eb = dsvc.EntropyBottleneck(N)
     eb.load_state_dict(eb_o.state_dict(), strict=False)
     eb, gc = eb.to(dev).eval(), dsvc.GaussianConditional(None).to(dev).eval()
     bits_ref = bits_got = 0.0
@@ -291,8 +294,8 @@ def test_iframe_codec_shapes_f4(oracle, hw):
         bits_ref += torch.log(zl_ref).sum().item()
         bits_got += torch.log(zl).sum().item()
         fused = zpart.sum().item()
-        for y_s, s_s, m_s in zip(y.chunk(10, 1), scales.chunk(10, 1), means.chunk(10, 1)):
-            assert y_s.shape[1] == 32
+        for y_s, s_s, m_s in zip(y.chunk(n_slices, 1), scales.chunk(n_slices, 1), means.chunk(n_slices, 1)):
+            assert y_s.shape[1] == M // n_slices
             _, lik_ref = gc_o(y_s, s_s, m_s)
             yh_ref = oracle.ste_round(y_s - m_s) + m_s
             yh, lik, part = gc.forward_fused(y_s.to(dev), s_s.to(dev), m_s.to(dev))
