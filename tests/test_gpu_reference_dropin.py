@@ -221,6 +221,72 @@ def test_forward_patched_vs_stock(reference_modules, size):
     assert rep["recon_max_abs_diff"] <= 1e-3
 
 
+def test_forward1_and_forward_msssim_patched_vs_stock(reference_modules, monkeypatch):
+    """The other callers of the path in ``video_model.py``: ``forward1`` (``:73-94``, warp at ``:83``; the
+    stage-1 training forward) and ``forward_msssim`` (``:96-135``, warp at ``:106``), stock vs patched;
+    then ``forward1`` in training mode with a backward pass (noise-mode entropy models, the 64-ch
+    feature warp's gradient with respect to the feature through the cell-order backward kernel).
+    MS-SSIM itself is outside the path (the shim has no implementation): a fixed stand-in is used
+    for both runs."""
+    import deepsvc_b200 as d
+    modules, image_model, video_model = reference_modules
+    H, W = 256, 448
+    model = _make_model(video_model)
+    ref, cur, sm, fea = _make_inputs(H, W)
+    monkeypatch.setattr(video_model, "ms_ssim", lambda a, b, data_range=1.0: 1.0 - torch.mean((a - b) ** 2))
+
+    def run_eval():
+        with torch.no_grad():
+            return model.forward1(ref, cur, sm, fea), model.forward_msssim(ref, cur, sm, fea)
+
+    def run_train():
+        model.train()
+        try:
+            torch.manual_seed(11)
+            f = fea.clone().requires_grad_(True)
+            model.zero_grad(set_to_none=True)
+            predict_frame, warp_loss, mc_loss, bpp_mv = model.forward1(ref, cur, sm, f)
+            (mc_loss + 0.1 * warp_loss + 0.01 * bpp_mv).backward()
+            pg = {n: p.grad.detach().clone() for n, p in model.named_parameters()
+                  if p.grad is not None and (n.startswith("mv_codec.g_a.0") or n.startswith("opticFlow.moduleBasic.0"))}
+            return f.grad.detach().clone(), pg, float(mc_loss.detach()), float(bpp_mv.detach())
+        finally:
+            model.eval()
+            model.zero_grad(set_to_none=True)
+
+    stock_e, stock_t, stock_t2 = run_eval(), run_train(), run_train()
+    try:
+        d.patch_reference(modules, video_model, image_model)
+        assert d.swap_entropy_models(model) == 4
+        patched_e, patched_t = run_eval(), run_train()
+    finally:
+        d.unpatch_reference()
+    rep = {}
+    # eval outputs: scalars within 1e-4 relative, images within 1e-3 absolute (conv inputs moved by ulps)
+    for which, names in ((0, ["predict_frame", "warp_loss", "mc_loss", "bpp_mv"]),
+                         (1, ["recon_image", "feature", "msssim", "warp_msssim", "mc_msssim", "bpp_res", "bpp_mv", "bpp"])):
+        for nm, a, b in zip(names, patched_e[which], stock_e[which]):
+            if a.dim() == 0:
+                rep[f"{which}:{nm}"] = _rel(a, b)
+                assert _rel(a, b) <= 1e-4, (nm, float(a), float(b))
+            else:
+                err = (a - b).abs().max().item()
+                rep[f"{which}:{nm}"] = err
+                assert err <= 1e-3 * max(1.0, b.abs().max().item()), (nm, err)
+    # training: losses and gradients against the stock run, with the stock run-to-run noise as the floor
+    def gdiff(x, y):
+        return (x - y).abs().max().item() / max(y.abs().max().item(), 1e-30)
+    floor = max([gdiff(stock_t2[0], stock_t[0])] + [gdiff(stock_t2[1][k], stock_t[1][k]) for k in stock_t[1]])
+    tol = max(1e-3, 20 * floor)
+    rep["train"] = {"mc_loss_rel": _rel(patched_t[2], stock_t[2]), "bpp_mv_rel": _rel(patched_t[3], stock_t[3]),
+                    "grad_feature": gdiff(patched_t[0], stock_t[0]), "stock_rerun_floor": floor,
+                    "grad_params": {k: gdiff(patched_t[1][k], stock_t[1][k]) for k in stock_t[1]}}
+    _dump("dropin_parity_forward1_train_256x448.json", rep)
+    assert rep["train"]["mc_loss_rel"] <= 1e-4 and rep["train"]["bpp_mv_rel"] <= 1e-4, rep["train"]
+    assert rep["train"]["grad_feature"] <= tol, rep["train"]
+    assert stock_t[1] and all(v <= tol for v in rep["train"]["grad_params"].values()), rep["train"]
+
+
 def test_compress_decompress_roundtrip_patched_and_streams_vs_stock(reference_modules):
     """``DeepSVC.compress`` -> ``decompress`` (``video_model.py:137-167``,
     ``image_model.py:201-302``) through the drop-in symbol pipeline and the C++ range coder;
