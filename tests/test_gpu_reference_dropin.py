@@ -239,26 +239,34 @@ def test_forward1_and_forward_msssim_patched_vs_stock(reference_modules, monkeyp
         with torch.no_grad():
             return model.forward1(ref, cur, sm, fea), model.forward_msssim(ref, cur, sm, fea)
 
-    def run_train():
+    def run_train(full=False):
         model.train()
         try:
             torch.manual_seed(11)
             f = fea.clone().requires_grad_(True)
             model.zero_grad(set_to_none=True)
-            predict_frame, warp_loss, mc_loss, bpp_mv = model.forward1(ref, cur, sm, f)
-            (mc_loss + 0.1 * warp_loss + 0.01 * bpp_mv).backward()
+            if full:   # DeepSVC.forward, the stage >= 4 training forward (Learner.py:1332-1343): both codecs
+                recon, feature, mse_loss, warp_loss, mc_loss, bpp_res, bpp_mv, bpp = model(ref, cur, sm, f)
+                (mse_loss + 0.1 * warp_loss + 0.1 * mc_loss + 0.01 * bpp).backward()
+                a, b_ = mse_loss, bpp
+            else:
+                predict_frame, warp_loss, mc_loss, bpp_mv = model.forward1(ref, cur, sm, f)
+                (mc_loss + 0.1 * warp_loss + 0.01 * bpp_mv).backward()
+                a, b_ = mc_loss, bpp_mv
             pg = {n: p.grad.detach().clone() for n, p in model.named_parameters()
-                  if p.grad is not None and (n.startswith("mv_codec.g_a.0") or n.startswith("opticFlow.moduleBasic.0"))}
-            return f.grad.detach().clone(), pg, float(mc_loss.detach()), float(bpp_mv.detach())
+                  if p.grad is not None and (n.startswith("mv_codec.g_a.0") or n.startswith("opticFlow.moduleBasic.0")
+                                             or n.startswith("res_codec.g_a.0"))}
+            return f.grad.detach().clone(), pg, float(a.detach()), float(b_.detach())
         finally:
             model.eval()
             model.zero_grad(set_to_none=True)
 
     stock_e, stock_t, stock_t2 = run_eval(), run_train(), run_train()
+    stock_f, stock_f2 = run_train(True), run_train(True)
     try:
         d.patch_reference(modules, video_model, image_model)
         assert d.swap_entropy_models(model) == 4
-        patched_e, patched_t = run_eval(), run_train()
+        patched_e, patched_t, patched_f = run_eval(), run_train(), run_train(True)
     finally:
         d.unpatch_reference()
     rep = {}
@@ -281,10 +289,18 @@ def test_forward1_and_forward_msssim_patched_vs_stock(reference_modules, monkeyp
     rep["train"] = {"mc_loss_rel": _rel(patched_t[2], stock_t[2]), "bpp_mv_rel": _rel(patched_t[3], stock_t[3]),
                     "grad_feature": gdiff(patched_t[0], stock_t[0]), "stock_rerun_floor": floor,
                     "grad_params": {k: gdiff(patched_t[1][k], stock_t[1][k]) for k in stock_t[1]}}
+    floor_f = max([gdiff(stock_f2[0], stock_f[0])] + [gdiff(stock_f2[1][k], stock_f[1][k]) for k in stock_f[1]])
+    tol_f = max(1e-3, 20 * floor_f)
+    rep["train_full_forward"] = {"mse_loss_rel": _rel(patched_f[2], stock_f[2]), "bpp_rel": _rel(patched_f[3], stock_f[3]),
+                                 "grad_feature": gdiff(patched_f[0], stock_f[0]), "stock_rerun_floor": floor_f,
+                                 "grad_params_max": max(gdiff(patched_f[1][k], stock_f[1][k]) for k in stock_f[1])}
     _dump("dropin_parity_forward1_train_256x448.json", rep)
     assert rep["train"]["mc_loss_rel"] <= 1e-4 and rep["train"]["bpp_mv_rel"] <= 1e-4, rep["train"]
     assert rep["train"]["grad_feature"] <= tol, rep["train"]
     assert stock_t[1] and all(v <= tol for v in rep["train"]["grad_params"].values()), rep["train"]
+    tf = rep["train_full_forward"]
+    assert tf["mse_loss_rel"] <= 1e-4 and tf["bpp_rel"] <= 1e-4, tf
+    assert tf["grad_feature"] <= tol_f and tf["grad_params_max"] <= tol_f and any(k.startswith("res_codec") for k in stock_f[1]), tf
 
 
 def test_compress_decompress_roundtrip_patched_and_streams_vs_stock(reference_modules):
